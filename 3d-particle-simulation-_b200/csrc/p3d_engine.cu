@@ -1,0 +1,707 @@
+// p3d_engine.cu — host side of the C ABI declared in include/p3d.h: device-buffer ownership,
+// type-sorted slot layout, per-step launch sequence, timing.  No CPU compute fallback exists:
+// every compute entry point needs the CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "p3d.h"
+#include "p3d_kernels_basic.cuh"
+#include "p3d_kernels_pair.cuh"
+
+static_assert(sizeof(p3d_particle) == 28, "boundary struct must be 28 bytes (src/lib.rs:12-17)");
+static_assert(sizeof(AosParticle) == 28, "device view of the boundary struct");
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(P3D_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                 \
+    } while (0)
+
+constexpr int kMaxTimedSteps = 512;
+constexpr int kRefTile = 128;       // threads per CTA of the reference-order kernel
+constexpr int kPairAutoMin = 4096;  // P3D_FORCE_AUTO switches to the pair kernel from this n
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return P3D_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = n + n / 8 + 64;  // grow-only with slack (host may add particles, main.rs:274-279)
+        CU(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+        return P3D_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct p3d_engine {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+
+    // layout
+    size_t n = 0;        // live particles
+    int n_slots = 0;     // padded slots (multiple of B)
+    int B = 128;         // block size in particles (32 * R) of the current layout
+    int B_next = 128;    // block size for the next upload (P3D_OPT_BLOCK_SIZE)
+    int M = 0;           // n_slots / B
+    uint32_t T = 0;      // id_count the layout was built for
+    std::vector<int> seg_start_h, seg_end_h;
+
+    DevBuf<float4> pos[2], vel, frc, spos;
+    DevBuf<uint32_t> perm, slot_of, sidx;
+    DevBuf<uint8_t> seg_type, bclass;
+    DevBuf<int> seg_start, seg_end, cnt;
+    DevBuf<float> aos, fout, sx, sy, sz;
+    DevBuf<float> matrix;
+    DevBuf<int> flags;      // [0],[1]: out-of-box flags (double-buffered by step parity)
+    DevBuf<double> diag;
+    int cur = 0;            // which pos buffer is current
+    int parity = 0;         // which flag word describes the current positions
+
+    // pinned staging for the one-shot call
+    void *pin = nullptr;
+    size_t pin_cap = 0;
+    std::vector<uint32_t> slot_h;
+
+    // options
+    int opt_force = P3D_FORCE_AUTO;
+    int opt_timing = 0;
+    int opt_graph = 0;
+    int opt_block_sort = 1;
+
+    // sharding
+    int rank = 0, world = 1;
+
+    // timing
+    std::vector<cudaEvent_t> ev;  // 3 per timed step: before force, after force, after integrate
+    int timed_steps = 0;
+    cudaEvent_t ev_call[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool call_timed = false;
+    float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t counters[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+int canonicalise(const p3d_params *prm, DevParams &P) {
+    if (!prm) return fail(P3D_ERR_INVALID, "params is null");
+    if (prm->id_count == 0 || prm->id_count > P3D_MAX_TYPES)
+        return fail(P3D_ERR_INVALID, "id_count %u outside 1..%d", prm->id_count, P3D_MAX_TYPES);
+    if (!prm->attraction_matrix) return fail(P3D_ERR_INVALID, "attraction_matrix is null");
+    // src/lib.rs:132  assert!(self.world_size >= 2.0 * self.particle_effect_radius)
+    if (!(prm->world_size >= 2.0f * prm->particle_effect_radius))
+        return fail(P3D_ERR_WORLD_TOO_SMALL, "world_size %g < 2 * particle_effect_radius %g (src/lib.rs:132)",
+                    prm->world_size, prm->particle_effect_radius);
+    P.W = prm->world_size;
+    P.half = prm->world_size * 0.5f;
+    P.r = prm->particle_effect_radius;
+    P.r2 = P.r * P.r;
+    P.m = prm->min_pull_ratio;
+    P.kf = prm->interaction_force;
+    P.coef = prm->coefficient;
+    P.ax = prm->accel[0];
+    P.ay = prm->accel[1];
+    P.az = prm->accel[2];
+    P.walls = prm->walls ? 1 : 0;
+    P.T = (int)prm->id_count;
+    const float m = P.m;
+    P.inv_m = (m > 0.0f) ? 1.0f / m : std::numeric_limits<float>::infinity();
+    if (m < 1.0f) {
+        P.c2 = 2.0f / (1.0f - m);
+        P.kk = (1.0f + m) / (1.0f - m);
+    } else {
+        P.c2 = 0.0f;
+        P.kk = 2.0f;
+    }
+    P.rcut = (P.r < 1.0f) ? 1 : 0;
+    P.reach = std::min(P.r, 1.0f);
+    return P3D_OK;
+}
+
+int ensure_pinned(p3d_engine *e, size_t bytes) {
+    if (bytes <= e->pin_cap) return P3D_OK;
+    if (e->pin) cudaFreeHost(e->pin);
+    e->pin = nullptr;
+    e->pin_cap = 0;
+    const size_t want = bytes + bytes / 8 + 4096;
+    CU(cudaMallocHost(&e->pin, want));
+    e->pin_cap = want;
+    return P3D_OK;
+}
+
+// Builds the type-sorted slot layout for `n` particles with ids `in[i].id` and uploads it.
+int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T) {
+    if (n > (size_t)0x7fff0000) return fail(P3D_ERR_INVALID, "n too large");
+    e->B = e->B_next;
+    const int B = e->B;
+    std::vector<size_t> count(T, 0);
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t id = in[i].id;
+        if (id >= T)
+            return fail(P3D_ERR_BAD_ID, "particle %zu has id %u >= id_count %u (src/lib.rs:225-228)", i, id, T);
+        ++count[id];
+    }
+    e->seg_start_h.assign(T, 0);
+    e->seg_end_h.assign(T, 0);
+    size_t at = 0;
+    for (uint32_t t = 0; t < T; ++t) {
+        e->seg_start_h[t] = (int)at;
+        at += (count[t] + B - 1) / B * B;
+        e->seg_end_h[t] = (int)at;
+    }
+    if (at == 0) at = B;  // keep one (ghost) block so kernels always have a valid grid
+    e->n_slots = (int)at;
+    e->M = e->n_slots / B;
+    e->n = n;
+    e->T = T;
+    std::vector<uint8_t> seg_type_h(e->M, 0);
+    for (uint32_t t = 0; t < T; ++t)
+        for (int b = e->seg_start_h[t] / B; b < e->seg_end_h[t] / B; ++b) seg_type_h[b] = (uint8_t)t;
+    e->slot_h.resize(n);
+    std::vector<size_t> cursor(T);
+    for (uint32_t t = 0; t < T; ++t) cursor[t] = (size_t)e->seg_start_h[t];
+    for (size_t i = 0; i < n; ++i) e->slot_h[i] = (uint32_t)cursor[in[i].id]++;  // stable within a type
+
+    const size_t ns = (size_t)e->n_slots;
+    int rc;
+    if ((rc = e->pos[0].ensure(ns))) return rc;
+    if ((rc = e->pos[1].ensure(ns))) return rc;
+    if ((rc = e->vel.ensure(ns))) return rc;
+    if ((rc = e->frc.ensure(ns))) return rc;
+    if ((rc = e->spos.ensure(ns))) return rc;
+    if ((rc = e->sidx.ensure(ns))) return rc;
+    if ((rc = e->sx.ensure(ns))) return rc;
+    if ((rc = e->sy.ensure(ns))) return rc;
+    if ((rc = e->sz.ensure(ns))) return rc;
+    if ((rc = e->perm.ensure(ns))) return rc;
+    if ((rc = e->slot_of.ensure(n ? n : 1))) return rc;
+    if ((rc = e->seg_type.ensure((size_t)e->M))) return rc;
+    if ((rc = e->bclass.ensure((size_t)e->M))) return rc;
+    if ((rc = e->seg_start.ensure(P3D_MAX_TYPES))) return rc;
+    if ((rc = e->seg_end.ensure(P3D_MAX_TYPES))) return rc;
+    if ((rc = e->cnt.ensure(2 * P3D_MAX_TYPES))) return rc;
+    if ((rc = e->aos.ensure((n ? n : 1) * 7))) return rc;
+    if ((rc = e->matrix.ensure(P3D_MAX_TYPES * P3D_MAX_TYPES))) return rc;
+    if ((rc = e->flags.ensure(4))) return rc;
+    if ((rc = e->diag.ensure(8))) return rc;
+
+    cudaStream_t st = e->stream;
+    CU(cudaMemcpyAsync(e->seg_type.p, seg_type_h.data(), (size_t)e->M, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->seg_start.p, e->seg_start_h.data(), T * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->seg_end.p, e->seg_end_h.data(), T * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (n) CU(cudaMemcpyAsync(e->slot_of.p, e->slot_h.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(e->flags.p, 0, 4 * sizeof(int), st));
+    // seg_type_h / slot_h are pageable: the copies above are staged synchronously by the runtime
+    CU(cudaStreamSynchronize(st));
+    return P3D_OK;
+}
+
+int launch_pack(p3d_engine *e, size_t n) {
+    cudaStream_t st = e->stream;
+    const int ns = e->n_slots;
+    e->cur = 0;
+    e->parity = 0;
+    k_fill_ghosts<<<(ns + 255) / 256, 256, 0, st>>>(e->pos[0].p, e->pos[1].p, e->vel.p, e->frc.p, e->perm.p, ns);
+    e->counters[0]++;
+    if (n) {
+        k_pack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->aos.p, e->slot_of.p, e->pos[0].p, e->vel.p,
+                                                            e->perm.p, (int)n);
+        e->counters[0]++;
+    }
+    CU(cudaGetLastError());
+    return P3D_OK;
+}
+
+int launch_unpack(p3d_engine *e, size_t n) {
+    if (!n) return P3D_OK;
+    k_unpack<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->pos[e->cur].p, e->vel.p, e->slot_of.p, e->aos.p,
+                                                                 (int)n);
+    e->counters[0]++;
+    CU(cudaGetLastError());
+    return P3D_OK;
+}
+
+int resolve_force_kernel(const p3d_engine *e) {
+    if (e->opt_force == P3D_FORCE_AUTO) return e->n >= (size_t)kPairAutoMin ? P3D_FORCE_PAIR : P3D_FORCE_REFERENCE_ORDER;
+    return e->opt_force;
+}
+
+size_t ref_smem(int tile, int T) { return (size_t)tile * sizeof(float4) + (size_t)T * T * sizeof(float); }
+
+// Force pass for the rows / slots of this shard.  Leaves total_force (src/lib.rs:177-243) in frc.
+int launch_force(p3d_engine *e, const DevParams &P) {
+    cudaStream_t st = e->stream;
+    const int ns = e->n_slots;
+    const int kind = resolve_force_kernel(e);
+    int *flag_cur = e->flags.p + e->parity;
+    int *flag_next = e->flags.p + (e->parity ^ 1);
+    const float4 *pos = e->pos[e->cur].p;
+    if (kind == P3D_FORCE_REFERENCE_ORDER) {
+        CU(cudaMemsetAsync(flag_next, 0, sizeof(int), st));
+        // shard: contiguous slot range
+        const int per = ((e->M + e->world - 1) / e->world) * e->B;
+        const int i0 = std::min(ns, e->rank * per), i1 = std::min(ns, i0 + per);
+        if (e->world > 1) CU(cudaMemsetAsync(e->frc.p, 0, (size_t)ns * sizeof(float4), st));
+        if (i1 > i0) {
+            k_force_ref<kRefTile><<<(i1 - i0 + kRefTile - 1) / kRefTile, kRefTile, ref_smem(kRefTile, P.T), st>>>(
+                pos, ns, i0, i1, e->frc.p, P, e->matrix.p, flag_cur, -1);
+            e->counters[0]++;
+            e->counters[1]++;
+        }
+        CU(cudaGetLastError());
+        return P3D_OK;
+    }
+    // --- pair path ---
+    const int B = e->B;
+    const float margin = std::max(1.0e-3f, 1.0e-5f * P.W);
+    const float interior_limit = e->opt_block_sort ? (P.half - P.reach - margin) : -1.0f;
+    CU(cudaMemsetAsync(e->cnt.p, 0, 2 * P3D_MAX_TYPES * sizeof(int), st));
+    k_part<<<(ns + 255) / 256, 256, 0, st>>>(pos, ns, B, e->seg_type.p, e->seg_start.p, e->seg_end.p, e->cnt.p,
+                                            e->spos.p, e->sx.p, e->sy.p, e->sz.p, e->sidx.p, interior_limit, flag_next);
+    k_part_fill<<<(ns + 255) / 256, 256, 0, st>>>(ns, B, e->seg_type.p, e->seg_start.p, e->seg_end.p, e->cnt.p,
+                                                 e->spos.p, e->sx.p, e->sy.p, e->sz.p, e->sidx.p, e->bclass.p);
+    CU(cudaMemsetAsync(e->frc.p, 0, (size_t)ns * sizeof(float4), st));
+    e->counters[0] += 2;
+
+    const int M = e->M;
+    const int rows = (M - e->rank + e->world - 1) / e->world;  // rows rank, rank+world, ...
+    if (rows > 0) {
+        const int nw = 4;
+        const int offsets = M / 2 + 1;
+        // enough CTAs for ~8 waves of 4 CTAs/SM, but never more warps than offsets in a row
+        int splits = (int)std::min<long long>((offsets + nw - 1) / nw,
+                                              std::max<long long>(1, (8LL * 4 * e->sm_count + rows - 1) / rows));
+        if (splits < 1) splits = 1;
+        const dim3 grid((unsigned)rows * (unsigned)splits);
+        if (B == 128) {
+            if (P.rcut)
+                k_force_pair<4, true><<<grid, nw * 32, 0, st>>>(e->sx.p, e->sy.p, e->sz.p, e->sidx.p, e->bclass.p, e->seg_type.p, M,
+                                                                e->rank, e->world, splits, e->frc.p, P,
+                                                                e->matrix.p, flag_cur);
+            else
+                k_force_pair<4, false><<<grid, nw * 32, 0, st>>>(e->sx.p, e->sy.p, e->sz.p, e->sidx.p, e->bclass.p, e->seg_type.p, M,
+                                                                 e->rank, e->world, splits, e->frc.p, P,
+                                                                 e->matrix.p, flag_cur);
+            k_force_bxb<128><<<rows, 128, ref_smem(128, P.T), st>>>(e->spos.p, e->sidx.p, e->bclass.p, M, e->rank,
+                                                                    e->world, e->seg_start.p, e->seg_end.p,
+                                                                    e->cnt.p, e->frc.p, P, e->matrix.p, flag_cur);
+        } else {
+            if (P.rcut)
+                k_force_pair<8, true><<<grid, nw * 32, 0, st>>>(e->sx.p, e->sy.p, e->sz.p, e->sidx.p, e->bclass.p, e->seg_type.p, M,
+                                                                e->rank, e->world, splits, e->frc.p, P,
+                                                                e->matrix.p, flag_cur);
+            else
+                k_force_pair<8, false><<<grid, nw * 32, 0, st>>>(e->sx.p, e->sy.p, e->sz.p, e->sidx.p, e->bclass.p, e->seg_type.p, M,
+                                                                 e->rank, e->world, splits, e->frc.p, P,
+                                                                 e->matrix.p, flag_cur);
+            k_force_bxb<256><<<rows, 256, ref_smem(256, P.T), st>>>(e->spos.p, e->sidx.p, e->bclass.p, M, e->rank,
+                                                                    e->world, e->seg_start.p, e->seg_end.p,
+                                                                    e->cnt.p, e->frc.p, P, e->matrix.p, flag_cur);
+        }
+        e->counters[0] += 2;
+        e->counters[1] += 2;
+    }
+    // out-of-box inputs (flag set): the reference-order kernel takes the whole step instead
+    {
+        const int per = ((M + e->world - 1) / e->world) * B;
+        const int i0 = std::min(ns, e->rank * per), i1 = std::min(ns, i0 + per);
+        if (i1 > i0) {
+            k_force_ref<kRefTile><<<(i1 - i0 + kRefTile - 1) / kRefTile, kRefTile, ref_smem(kRefTile, P.T), st>>>(
+                pos, ns, i0, i1, e->frc.p, P, e->matrix.p, flag_cur, 1);
+            e->counters[0]++;
+        }
+    }
+    CU(cudaGetLastError());
+    return P3D_OK;
+}
+
+int launch_integrate(p3d_engine *e, const DevParams &P, float ts) {
+    const int ns = e->n_slots;
+    int s0 = 0, s1 = ns;
+    if (e->world > 1) {
+        const int per = ((e->M + e->world - 1) / e->world) * e->B;
+        s0 = std::min(ns, e->rank * per);
+        s1 = std::min(ns, s0 + per);
+    }
+    if (s1 > s0) {
+        k_integrate<<<(s1 - s0 + 255) / 256, 256, 0, e->stream>>>(e->pos[e->cur].p, e->pos[e->cur ^ 1].p, e->vel.p,
+                                                                  e->frc.p, s0, s1, P, ts,
+                                                                  e->flags.p + (e->parity ^ 1));
+        e->counters[0]++;
+        e->counters[2]++;
+    }
+    CU(cudaGetLastError());
+    return P3D_OK;
+}
+
+int upload_matrix(p3d_engine *e, const p3d_params *prm) {
+    const size_t bytes = (size_t)prm->id_count * prm->id_count * sizeof(float);
+    // pageable source: staged synchronously by the runtime, so the caller's array may change afterwards
+    CU(cudaMemcpyAsync(e->matrix.p, prm->attraction_matrix, bytes, cudaMemcpyHostToDevice, e->stream));
+    return P3D_OK;
+}
+
+int ensure_events(p3d_engine *e, int steps) {
+    const size_t need = (size_t)std::min(steps, kMaxTimedSteps) * 3;
+    while (e->ev.size() < need) {
+        cudaEvent_t x;
+        CU(cudaEventCreate(&x));
+        e->ev.push_back(x);
+    }
+    for (int k = 0; k < 6; ++k)
+        if (!e->ev_call[k]) CU(cudaEventCreate(&e->ev_call[k]));
+    return P3D_OK;
+}
+
+int check_box_now(p3d_engine *e, const DevParams &P) {
+    int *flag_cur = e->flags.p + e->parity;
+    CU(cudaMemsetAsync(flag_cur, 0, sizeof(int), e->stream));
+    k_check_box<<<(e->n_slots + 255) / 256, 256, 0, e->stream>>>(e->pos[e->cur].p, e->n_slots, P.half, flag_cur);
+    e->counters[0]++;
+    CU(cudaGetLastError());
+    return P3D_OK;
+}
+
+int run_steps(p3d_engine *e, const p3d_params *prm, const DevParams &P, float ts, int n_steps) {
+    int rc;
+    if ((rc = upload_matrix(e, prm))) return rc;
+    if ((rc = check_box_now(e, P))) return rc;  // world_size may have changed since the last call
+    e->timed_steps = 0;
+    if (e->opt_timing && (rc = ensure_events(e, n_steps))) return rc;
+    for (int s = 0; s < n_steps; ++s) {
+        const bool timed = e->opt_timing && s < kMaxTimedSteps;
+        if (timed) CU(cudaEventRecord(e->ev[3 * s], e->stream));
+        if ((rc = launch_force(e, P))) return rc;
+        if (timed) CU(cudaEventRecord(e->ev[3 * s + 1], e->stream));
+        if ((rc = launch_integrate(e, P, ts))) return rc;
+        if (timed) {
+            CU(cudaEventRecord(e->ev[3 * s + 2], e->stream));
+            e->timed_steps = s + 1;
+        }
+        e->cur ^= 1;
+        e->parity ^= 1;
+    }
+    return P3D_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int p3d_abi_version(void) { return P3D_ABI_VERSION; }
+
+const char *p3d_last_error(void) { return g_last_error.c_str(); }
+
+int p3d_create(int device, p3d_engine **out) {
+    if (!out) return fail(P3D_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(P3D_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail(P3D_ERR_NO_DEVICE, "device %d not in 0..%d", device, count - 1);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(P3D_ERR_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major,
+                    prop.minor);
+    p3d_engine *e = new p3d_engine();
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    *out = e;
+    return P3D_OK;
+}
+
+void p3d_destroy(p3d_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (auto &b : e->pos) b.release();
+    e->vel.release(); e->frc.release(); e->spos.release();
+    e->perm.release(); e->slot_of.release(); e->sidx.release();
+    e->seg_type.release(); e->bclass.release();
+    e->seg_start.release(); e->seg_end.release(); e->cnt.release();
+    e->aos.release(); e->fout.release(); e->sx.release(); e->sy.release(); e->sz.release(); e->matrix.release(); e->flags.release(); e->diag.release();
+    if (e->pin) cudaFreeHost(e->pin);
+    for (auto x : e->ev) cudaEventDestroy(x);
+    for (auto x : e->ev_call) if (x) cudaEventDestroy(x);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+int p3d_set_stream(p3d_engine *e, void *cuda_stream) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return P3D_OK;
+}
+
+int p3d_set_option(p3d_engine *e, int option, int value) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    switch (option) {
+        case P3D_OPT_FORCE_KERNEL:
+            if (value < P3D_FORCE_AUTO || value > P3D_FORCE_PAIR) return fail(P3D_ERR_INVALID, "bad force kernel %d", value);
+            e->opt_force = value;
+            return P3D_OK;
+        case P3D_OPT_TIMING: e->opt_timing = value ? 1 : 0; return P3D_OK;
+        case P3D_OPT_GRAPH: e->opt_graph = value ? 1 : 0; return P3D_OK;
+        case P3D_OPT_BLOCK_SORT: e->opt_block_sort = value ? 1 : 0; return P3D_OK;
+        case P3D_OPT_BLOCK_SIZE:
+            if (value != 128 && value != 256) return fail(P3D_ERR_INVALID, "block size must be 128 or 256");
+            e->B_next = value;
+            return P3D_OK;
+        default: return fail(P3D_ERR_INVALID, "unknown option %d", option);
+    }
+}
+
+int p3d_get_option(p3d_engine *e, int option, int *value) {
+    if (!e || !value) return fail(P3D_ERR_INVALID, "null argument");
+    switch (option) {
+        case P3D_OPT_FORCE_KERNEL: *value = e->opt_force; return P3D_OK;
+        case P3D_OPT_TIMING: *value = e->opt_timing; return P3D_OK;
+        case P3D_OPT_GRAPH: *value = e->opt_graph; return P3D_OK;
+        case P3D_OPT_BLOCK_SORT: *value = e->opt_block_sort; return P3D_OK;
+        case P3D_OPT_BLOCK_SIZE: *value = e->B_next; return P3D_OK;
+        default: return fail(P3D_ERR_INVALID, "unknown option %d", option);
+    }
+}
+
+int p3d_upload(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t id_count) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (n && !in) return fail(P3D_ERR_INVALID, "in is null");
+    if (id_count == 0 || id_count > P3D_MAX_TYPES)
+        return fail(P3D_ERR_INVALID, "id_count %u outside 1..%d", id_count, P3D_MAX_TYPES);
+    CU(cudaSetDevice(e->device));
+    int rc;
+    if ((rc = build_layout(e, in, n, id_count))) return rc;
+    if (e->opt_timing) {
+        if ((rc = ensure_events(e, 1))) return rc;
+        CU(cudaEventRecord(e->ev_call[0], e->stream));
+    }
+    if (n) CU(cudaMemcpyAsync(e->aos.p, in, n * sizeof(p3d_particle), cudaMemcpyHostToDevice, e->stream));
+    if (e->opt_timing) CU(cudaEventRecord(e->ev_call[1], e->stream));
+    if ((rc = launch_pack(e, n))) return rc;
+    if (e->opt_timing) CU(cudaEventRecord(e->ev_call[2], e->stream));
+    // `in` may be pageable: make sure the copy has consumed it before returning to the caller
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->opt_timing) {
+        CU(cudaEventElapsedTime(&e->last_ms[5], e->ev_call[0], e->ev_call[1]));
+        CU(cudaEventElapsedTime(&e->last_ms[2], e->ev_call[1], e->ev_call[2]));
+    }
+    return P3D_OK;
+}
+
+int p3d_step(p3d_engine *e, const p3d_params *prm, float ts, int n_steps) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (n_steps < 0) return fail(P3D_ERR_INVALID, "n_steps < 0");
+    DevParams P;
+    int rc;
+    if ((rc = canonicalise(prm, P))) return rc;
+    if (prm->id_count != e->T && e->n > 0)
+        return fail(P3D_ERR_INVALID, "id_count %u differs from the uploaded layout (%u): upload again", prm->id_count,
+                    e->T);
+    if (e->n_slots == 0) return fail(P3D_ERR_INVALID, "no particles uploaded");
+    CU(cudaSetDevice(e->device));
+    return run_steps(e, prm, P, ts, n_steps);
+}
+
+int p3d_sync(p3d_engine *e) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    return P3D_OK;
+}
+
+int p3d_download(p3d_engine *e, p3d_particle *out, size_t n) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (n != e->n) return fail(P3D_ERR_INVALID, "n=%zu but %zu particles are resident", n, e->n);
+    if (n && !out) return fail(P3D_ERR_INVALID, "out is null");
+    CU(cudaSetDevice(e->device));
+    int rc;
+    if (e->opt_timing) {
+        if ((rc = ensure_events(e, 1))) return rc;
+        CU(cudaEventRecord(e->ev_call[3], e->stream));
+    }
+    if ((rc = launch_unpack(e, n))) return rc;
+    if (e->opt_timing) CU(cudaEventRecord(e->ev_call[4], e->stream));
+    if (n) CU(cudaMemcpyAsync(out, e->aos.p, n * sizeof(p3d_particle), cudaMemcpyDeviceToHost, e->stream));
+    if (e->opt_timing) CU(cudaEventRecord(e->ev_call[5], e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->opt_timing) {
+        CU(cudaEventElapsedTime(&e->last_ms[3], e->ev_call[3], e->ev_call[4]));
+        CU(cudaEventElapsedTime(&e->last_ms[6], e->ev_call[4], e->ev_call[5]));
+    }
+    return P3D_OK;
+}
+
+int p3d_download_forces(p3d_engine *e, float *out_xyz, size_t n) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (n != e->n) return fail(P3D_ERR_INVALID, "n=%zu but %zu particles are resident", n, e->n);
+    if (!n) return P3D_OK;
+    if (!out_xyz) return fail(P3D_ERR_INVALID, "out is null");
+    CU(cudaSetDevice(e->device));
+    int rc;
+    if ((rc = e->fout.ensure(n * 3))) return rc;
+    k_unpack_forces<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->frc.p, e->slot_of.p, e->fout.p, (int)n);
+    e->counters[0]++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_xyz, e->fout.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return P3D_OK;
+}
+
+int p3d_update(p3d_engine *e, const p3d_params *prm, float ts, const p3d_particle *in, p3d_particle *out, size_t n) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    DevParams P;
+    int rc;
+    if ((rc = canonicalise(prm, P))) return rc;  // src/lib.rs:132 comes first in the reference too
+    if (n == 0) return P3D_OK;                   // src/lib.rs:135-171 with an empty Vec is a no-op
+    if (!in || !out) return fail(P3D_ERR_INVALID, "in/out is null");
+    CU(cudaSetDevice(e->device));
+    if ((rc = p3d_upload(e, in, n, prm->id_count))) return rc;
+    if ((rc = run_steps(e, prm, P, ts, 1))) return rc;
+    if ((rc = p3d_download(e, out, n))) return rc;
+    return P3D_OK;
+}
+
+int p3d_diagnostics(p3d_engine *e, double out[8]) {
+    if (!e || !out) return fail(P3D_ERR_INVALID, "null argument");
+    if (e->n_slots == 0) return fail(P3D_ERR_INVALID, "no particles uploaded");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemsetAsync(e->diag.p, 0, 8 * sizeof(double), e->stream));
+    const int blocks = std::min(4 * e->sm_count, (e->n_slots + 255) / 256);
+    k_diag<<<blocks, 256, 0, e->stream>>>(e->pos[e->cur].p, e->vel.p, e->n_slots, e->diag.p);
+    e->counters[0]++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, e->diag.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return P3D_OK;
+}
+
+int p3d_get_timing(p3d_engine *e, float ms[8]) {
+    if (!e || !ms) return fail(P3D_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    float f = 0.f, g = 0.f;
+    for (int s = 0; s < e->timed_steps; ++s) {
+        float a = 0.f, b = 0.f;
+        CU(cudaEventElapsedTime(&a, e->ev[3 * s], e->ev[3 * s + 1]));
+        CU(cudaEventElapsedTime(&b, e->ev[3 * s + 1], e->ev[3 * s + 2]));
+        f += a;
+        g += b;
+    }
+    e->last_ms[0] = f;
+    e->last_ms[1] = g;
+    e->last_ms[7] = f + g;
+    std::memcpy(ms, e->last_ms, sizeof(e->last_ms));
+    return P3D_OK;
+}
+
+int p3d_get_counters(p3d_engine *e, uint64_t out[4]) {
+    if (!e || !out) return fail(P3D_ERR_INVALID, "null argument");
+    std::memcpy(out, e->counters, sizeof(e->counters));
+    return P3D_OK;
+}
+
+int p3d_device_buffer(p3d_engine *e, int which, void **dev_ptr, size_t *n_slots) {
+    if (!e || !dev_ptr) return fail(P3D_ERR_INVALID, "null argument");
+    if (e->n_slots == 0) return fail(P3D_ERR_INVALID, "no particles uploaded");
+    switch (which) {
+        case P3D_BUF_POS: *dev_ptr = e->pos[e->cur].p; break;
+        case P3D_BUF_POS_NEXT: *dev_ptr = e->pos[e->cur ^ 1].p; break;
+        case P3D_BUF_VEL: *dev_ptr = e->vel.p; break;
+        case P3D_BUF_FORCE: *dev_ptr = e->frc.p; break;
+        default: return fail(P3D_ERR_INVALID, "unknown buffer %d", which);
+    }
+    if (n_slots) *n_slots = (size_t)e->n_slots;
+    return P3D_OK;
+}
+
+int p3d_set_shard(p3d_engine *e, int rank, int world) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (world < 1 || rank < 0 || rank >= world) return fail(P3D_ERR_INVALID, "bad shard %d/%d", rank, world);
+    e->rank = rank;
+    e->world = world;
+    return P3D_OK;
+}
+
+int p3d_shard_range(p3d_engine *e, size_t *slot_begin, size_t *slot_end) {
+    if (!e || !slot_begin || !slot_end) return fail(P3D_ERR_INVALID, "null argument");
+    const int per = ((e->M + e->world - 1) / e->world) * e->B;
+    const int s0 = std::min(e->n_slots, e->rank * per);
+    *slot_begin = (size_t)s0;
+    *slot_end = (size_t)std::min(e->n_slots, s0 + per);
+    return P3D_OK;
+}
+
+int p3d_shard_force(p3d_engine *e, const p3d_params *prm) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    DevParams P;
+    int rc;
+    if ((rc = canonicalise(prm, P))) return rc;
+    if (e->n_slots == 0) return fail(P3D_ERR_INVALID, "no particles uploaded");
+    CU(cudaSetDevice(e->device));
+    if ((rc = upload_matrix(e, prm))) return rc;
+    // the out-of-box flag written by this rank's integrate covers only its own shard; after the
+    // driver's all-gather every rank re-derives it from the full position array
+    if ((rc = check_box_now(e, P))) return rc;
+    return launch_force(e, P);
+}
+
+int p3d_shard_integrate(p3d_engine *e, const p3d_params *prm, float ts) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    DevParams P;
+    int rc;
+    if ((rc = canonicalise(prm, P))) return rc;
+    CU(cudaSetDevice(e->device));
+    return launch_integrate(e, P, ts);
+}
+
+int p3d_shard_commit(p3d_engine *e) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    e->cur ^= 1;
+    e->parity ^= 1;
+    return P3D_OK;
+}
+
+}  // extern "C"

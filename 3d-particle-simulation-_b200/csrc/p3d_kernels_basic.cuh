@@ -1,0 +1,269 @@
+// p3d_kernels_basic.cuh — layout conversion (K3), reference-order force (K1-ref), fused
+// integration (K2), diagnostics (K4).  All hand-written for sm_100a.
+#pragma once
+#include "p3d_device.cuh"
+
+// The 28-byte boundary struct (include/p3d.h p3d_particle), seen as 7 words.
+struct AosParticle {
+    float px, py, pz, vx, vy, vz;
+    uint32_t id;
+};
+
+// ---------------------------------------------------------------------------------------------
+// K3a: fill every slot with a ghost (both position buffers), zero velocity/force, perm = ghost.
+__global__ void __launch_bounds__(256) k_fill_ghosts(float4 *__restrict__ pos0, float4 *__restrict__ pos1,
+                                                     float4 *__restrict__ vel, float4 *__restrict__ frc,
+                                                     uint32_t *__restrict__ perm, int n_slots) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    const float4 g = make_float4(P3D_GHOST_COORD, P3D_GHOST_COORD, P3D_GHOST_COORD, u2f(P3D_GHOST_ID));
+    pos0[s] = g;
+    pos1[s] = g;
+    vel[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    frc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    perm[s] = P3D_GHOST_ID;
+}
+
+// K3b: AoS (28 B, caller's index order) -> SoA float4 slots (type-sorted).  The block stages its
+// 256 structs through shared memory so that the global reads are fully coalesced 4-byte streams;
+// the per-thread reads from shared memory have stride 7 words (co-prime with 32 banks).
+__global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, const uint32_t *__restrict__ slot_of,
+                                              float4 *__restrict__ pos, float4 *__restrict__ vel,
+                                              uint32_t *__restrict__ perm, int n) {
+    __shared__ float sm[256 * 7];
+    const int base = blockIdx.x * 256;
+    const int cnt = min(256, n - base);
+    const float *src = aos + (size_t)base * 7;
+    for (int w = threadIdx.x; w < cnt * 7; w += 256) sm[w] = src[w];
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= cnt) return;
+    const float *p = sm + t * 7;
+    const uint32_t s = slot_of[base + t];
+    pos[s] = make_float4(p[0], p[1], p[2], p[6]);  // w carries the id bits
+    vel[s] = make_float4(p[3], p[4], p[5], 0.f);
+    perm[s] = (uint32_t)(base + t);
+}
+
+// K3c: SoA slots -> AoS in the caller's index order (src/lib.rs:268: index order preserved).
+__global__ void __launch_bounds__(256) k_unpack(const float4 *__restrict__ pos, const float4 *__restrict__ vel,
+                                                const uint32_t *__restrict__ slot_of, float *__restrict__ aos,
+                                                int n) {
+    __shared__ float sm[256 * 7];
+    const int base = blockIdx.x * 256;
+    const int cnt = min(256, n - base);
+    const int t = threadIdx.x;
+    if (t < cnt) {
+        const uint32_t s = slot_of[base + t];
+        const float4 p = pos[s];
+        const float4 v = vel[s];
+        float *o = sm + t * 7;
+        o[0] = p.x; o[1] = p.y; o[2] = p.z;
+        o[3] = v.x; o[4] = v.y; o[5] = v.z;
+        o[6] = p.w;
+    }
+    __syncthreads();
+    float *dst = aos + (size_t)base * 7;
+    for (int w = threadIdx.x; w < cnt * 7; w += 256) dst[w] = sm[w];
+}
+
+// Forces in caller order (n*3 floats) for tests.
+__global__ void __launch_bounds__(256) k_unpack_forces(const float4 *__restrict__ frc,
+                                                       const uint32_t *__restrict__ slot_of,
+                                                       float *__restrict__ out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 f = frc[slot_of[i]];
+    out[3 * i] = f.x; out[3 * i + 1] = f.y; out[3 * i + 2] = f.z;
+}
+
+// Sets flags[0] |= 1 when some particle lies outside [-W/2, W/2]^3.  The fast force kernel assumes
+// in-box positions (then only two images per axis can be in range); otherwise the reference-order
+// kernel, which searches all three images per axis like src/lib.rs:177-185, takes the step.
+__global__ void __launch_bounds__(256) k_check_box(const float4 *__restrict__ pos, int n_slots, float half,
+                                                   int *__restrict__ flags) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    const float4 p = pos[s];
+    if (f2u(p.w) == P3D_GHOST_ID) return;
+    if (!(fabsf(p.x) <= half && fabsf(p.y) <= half && fabsf(p.z) <= half)) atomicOr(flags, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact piecewise force law, src/lib.rs:55-67, IEEE ops in the reference's order (no contraction).
+__device__ __forceinline__ float ref_calculate_force(float m, float d, float a) {
+    if (d < m) {
+        return __fsub_rn(__fdiv_rn(d, m), 1.0f);
+    } else if (m < d && d < 1.0f) {
+        float t = __fmul_rn(2.0f, d);
+        t = __fsub_rn(t, 1.0f);
+        t = __fsub_rn(t, m);
+        return __fmul_rn(a, __fsub_rn(1.0f, __fdiv_rn(fabsf(t), __fsub_rn(1.0f, m))));
+    }
+    return 0.0f;
+}
+
+// Picks, per axis, the periodic image of the i-particle closest to q.  The three candidates are
+// exactly the reference's `other.position - (position + offset)` for offset in {-W, 0, +W}
+// (src/lib.rs:190-191,211-212), including the f32 rounding of position + offset.  Because
+// W >= 2r (src/lib.rs:132) at most one candidate per axis can satisfy |rel| < r, so taking the
+// smallest |rel| visits the same (particle, image) pairs as the 27-image loop.
+__device__ __forceinline__ float nearest_image3(float q, float p0, float pm, float pp) {
+    const float r0 = __fsub_rn(q, p0), rm = __fsub_rn(q, pm), rp = __fsub_rn(q, pp);
+    float best = r0;
+    if (fabsf(rm) < fabsf(best)) best = rm;
+    if (fabsf(rp) < fabsf(best)) best = rp;
+    return best;
+}
+
+// K1-ref: one thread per i-particle, j-tiles staged in shared memory, exact sqrt and divides,
+// operations in the reference's order (src/lib.rs:211-231).  Used for small N, for out-of-box
+// inputs, and as the on-device cross-check of the fast kernel at sizes the CPU oracle cannot reach.
+// only_flag >= 0: run only when flags[0] == only_flag (device-side dispatch, no host sync).
+template <int TILE>
+__global__ void __launch_bounds__(TILE) k_force_ref(const float4 *__restrict__ pos, int n_slots, int i_begin,
+                                                    int i_end, float4 *__restrict__ frc, DevParams P,
+                                                    const float *__restrict__ matrix,
+                                                    const int *__restrict__ flags, int only_flag) {
+    if (only_flag >= 0 && flags[0] != only_flag) return;
+    extern __shared__ float4 sm_dyn[];
+    float4 *tile = sm_dyn;
+    float *smat = reinterpret_cast<float *>(sm_dyn + TILE);
+    for (int k = threadIdx.x; k < P.T * P.T; k += TILE) smat[k] = matrix[k];
+
+    const int i = i_begin + blockIdx.x * TILE + threadIdx.x;
+    float4 pi = make_float4(P3D_GHOST_COORD, P3D_GHOST_COORD, P3D_GHOST_COORD, u2f(P3D_GHOST_ID));
+    if (i < i_end) pi = pos[i];
+    const uint32_t idi = f2u(pi.w);
+    const bool live = idi != P3D_GHOST_ID;
+    // position + offset for offset = -W, +W (offset 0 leaves the position unchanged)
+    const float pxm = __fadd_rn(pi.x, -P.W), pxp = __fadd_rn(pi.x, P.W);
+    const float pym = __fadd_rn(pi.y, -P.W), pyp = __fadd_rn(pi.y, P.W);
+    const float pzm = __fadd_rn(pi.z, -P.W), pzp = __fadd_rn(pi.z, P.W);
+    const uint32_t row = live ? idi * (uint32_t)P.T : 0u;
+
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int j0 = 0; j0 < n_slots; j0 += TILE) {
+        __syncthreads();
+        const int j = j0 + threadIdx.x;
+        tile[threadIdx.x] = (j < n_slots)
+                                ? pos[j]
+                                : make_float4(P3D_GHOST_COORD, P3D_GHOST_COORD, P3D_GHOST_COORD, u2f(P3D_GHOST_ID));
+        __syncthreads();
+        if (!live) continue;
+#pragma unroll 4
+        for (int t = 0; t < TILE; ++t) {
+            const float4 q = tile[t];
+            const float rx = nearest_image3(q.x, pi.x, pxm, pxp);
+            const float ry = nearest_image3(q.y, pi.y, pym, pyp);
+            const float rz = nearest_image3(q.z, pi.z, pzm, pzp);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
+            if (d2 > 0.0f && d2 < P.r2) {  // src/lib.rs:216-220
+                const float d = __fsqrt_rn(d2);
+                const float a = smat[row + f2u(q.w)];
+                const float f = ref_calculate_force(P.m, d, a);
+                ax = __fadd_rn(ax, __fmul_rn(__fdiv_rn(rx, d), f));  // src/lib.rs:231
+                ay = __fadd_rn(ay, __fmul_rn(__fdiv_rn(ry, d), f));
+                az = __fadd_rn(az, __fmul_rn(__fdiv_rn(rz, d), f));
+            }
+        }
+    }
+    if (i < i_end) frc[i] = make_float4(ax, ay, az, 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: kick + gravity + drag + drift + wall/wrap, fused (src/lib.rs:245-264 and :70-127), bit-for-bit
+// the reference's operation order.  Bandwidth bound: reads pos, vel, force (48 B), writes pos, vel
+// (32 B) = 80 B per particle.
+__device__ __forceinline__ void wall_axis(float half, float W, int walls, float &p, float &v) {
+    if (p > half) {
+        if (walls) { p = half; v = fminf(v, 0.0f); }
+        else       { p = __fsub_rn(p, W); }
+    } else if (p < -half) {
+        if (walls) { p = -half; v = fmaxf(v, 0.0f); }
+        else       { p = __fadd_rn(p, W); }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_integrate(const float4 *__restrict__ pos, float4 *__restrict__ pos_next,
+                                                   float4 *__restrict__ vel, const float4 *__restrict__ frc,
+                                                   int s_begin, int s_end, DevParams P, float ts,
+                                                   int *__restrict__ flag_next) {
+    const int s = s_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= s_end) return;
+    float4 p = pos[s];
+    if (f2u(p.w) == P3D_GHOST_ID) return;  // ghosts are identical in both position buffers
+    float4 v = vel[s];
+    const float4 F = frc[s];
+    // :246-247  velocity += ((F * k) * r) * ts
+    v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(__fmul_rn(F.x, P.kf), P.r), ts));
+    v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(__fmul_rn(F.y, P.kf), P.r), ts));
+    v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(__fmul_rn(F.z, P.kf), P.r), ts));
+    // :249  velocity += acceleration * ts
+    v.x = __fadd_rn(v.x, __fmul_rn(P.ax, ts));
+    v.y = __fadd_rn(v.y, __fmul_rn(P.ay, ts));
+    v.z = __fadd_rn(v.z, __fmul_rn(P.az, ts));
+    // :252-259  drag with stop clamp
+    const float cx = __fmul_rn(__fmul_rn(v.x, P.coef), ts);
+    const float cy = __fmul_rn(__fmul_rn(v.y, P.coef), ts);
+    const float cz = __fmul_rn(__fmul_rn(v.z, P.coef), ts);
+    const float c2 = __fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz));
+    const float v2 = __fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z));
+    if (c2 > v2) {
+        v.x = 0.f; v.y = 0.f; v.z = 0.f;
+    } else {
+        v.x = __fsub_rn(v.x, cx); v.y = __fsub_rn(v.y, cy); v.z = __fsub_rn(v.z, cz);
+    }
+    // :262  position += velocity * ts
+    p.x = __fadd_rn(p.x, __fmul_rn(v.x, ts));
+    p.y = __fadd_rn(p.y, __fmul_rn(v.y, ts));
+    p.z = __fadd_rn(p.z, __fmul_rn(v.z, ts));
+    // :264 -> :70-127
+    wall_axis(P.half, P.W, P.walls, p.x, v.x);
+    wall_axis(P.half, P.W, P.walls, p.y, v.y);
+    wall_axis(P.half, P.W, P.walls, p.z, v.z);
+    if (!(fabsf(p.x) <= P.half && fabsf(p.y) <= P.half && fabsf(p.z) <= P.half)) atomicOr(flag_next, 1);
+    pos_next[s] = p;
+    vel[s] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: diagnostics (the reference has none; needed for the 1,000-step drift check).
+// out[0]=sum 0.5|v|^2  out[1..3]=sum v  out[4]=max|v|^2  out[5]=count  out[6]=sum|p|^2
+__global__ void __launch_bounds__(256) k_diag(const float4 *__restrict__ pos, const float4 *__restrict__ vel,
+                                              int n_slots, double *__restrict__ out) {
+    double ke = 0, sx = 0, sy = 0, sz = 0, mx = 0, cnt = 0, pp = 0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
+        const float4 p = pos[s];
+        if (f2u(p.w) == P3D_GHOST_ID) continue;
+        const float4 v = vel[s];
+        const double v2 = (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z;
+        ke += 0.5 * v2; sx += v.x; sy += v.y; sz += v.z;
+        mx = fmax(mx, v2); cnt += 1.0;
+        pp += (double)p.x * p.x + (double)p.y * p.y + (double)p.z * p.z;
+    }
+    __shared__ double red[7][8];
+    double vals[7] = {ke, sx, sy, sz, mx, cnt, pp};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        double x = vals[k];
+        for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_down_sync(0xffffffffu, x, o);
+            x = (k == 4) ? fmax(x, y) : x + y;
+        }
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        const int k = threadIdx.x;
+        double x = red[k][0];
+        for (int w = 1; w < 8; ++w) x = (k == 4) ? fmax(x, red[k][w]) : x + red[k][w];
+        if (k == 4) {
+            // max via CAS on the bit pattern (values are non-negative, so the ordering of the
+            // unsigned patterns equals the ordering of the doubles)
+            atomicMax(reinterpret_cast<unsigned long long *>(out + 4), (unsigned long long)__double_as_longlong(x));
+        } else {
+            atomicAdd(out + k, x);
+        }
+    }
+}

@@ -1,0 +1,317 @@
+// p3d_kernels_pair.cuh — the fast all-pairs force pass (K1) for sm_100a.
+//
+// Replaces the spatial-hash neighbour walk of src/lib.rs:135-243 with an evaluation of ALL
+// particle pairs.  Design:
+//   * Slots are grouped in blocks of B = 32*R particles of ONE type.  Every step a partition pass
+//     stages each type's particles as [interior ... ghosts ... boundary]; a block is INTERIOR when
+//     every member is farther than reach=min(r,1) from every face, so that only the offset-0 image
+//     of src/lib.rs:177-185 can be in range for any pair that involves it.
+//   * k_force_pair visits every unordered block pair {a,b} with at least one INTERIOR member once
+//     (circulant schedule: row a takes b = a+o, o = 0..M/2).  Inside a pair the relative position,
+//     distance, rsqrt and the type-independent part of the force law are shared by both directions
+//     (the attraction matrix is asymmetric, src/bin/main.rs:133-139, so only the scalar differs).
+//     A warp keeps R i-particles per lane in registers; 64 j-particles per round travel around
+//     the warp with shuffles together with their force accumulators, so neither side ever needs a
+//     cross-lane reduction.  All arithmetic is packed FP32x2 (FADD2/FFMA2): two j per instruction.
+//   * BOUNDARY x BOUNDARY block pairs (the only ones that can interact through a periodic image)
+//     go to k_force_bxb, which reproduces the reference's image arithmetic exactly.
+#pragma once
+#include "p3d_device.cuh"
+#include "p3d_kernels_basic.cuh"
+
+enum : uint8_t { P3D_BLK_INTERIOR = 0, P3D_BLK_BOUNDARY = 1, P3D_BLK_EMPTY = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// Partition pass, part 1: stage every live slot into its type's region of the block list —
+// interior particles packed upward from the region start, boundary particles downward from its
+// end.  One warp covers 32 consecutive slots, which always share a type (segments are padded to
+// multiples of B >= 32), so a single atomic per class per warp reserves the destinations.
+__global__ void __launch_bounds__(256) k_part(const float4 *__restrict__ pos, int n_slots, int B,
+                                              const uint8_t *__restrict__ seg_type,
+                                              const int *__restrict__ seg_start, const int *__restrict__ seg_end,
+                                              int *__restrict__ cnt, float4 *__restrict__ spos,
+                                              float *__restrict__ sx, float *__restrict__ sy,
+                                              float *__restrict__ sz, uint32_t *__restrict__ sidx,
+                                              float interior_limit, int *__restrict__ flag_to_clear) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) *flag_to_clear = 0;
+    if (s >= n_slots) return;  // n_slots is a multiple of 32: whole warps leave together
+    const float4 p = pos[s];
+    const bool live = f2u(p.w) != P3D_GHOST_ID;
+    const int t = seg_type[s / B];
+    const float amax = fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z)));
+    const bool interior = live && (amax < interior_limit);
+    const bool boundary = live && !interior;
+    const unsigned mi = __ballot_sync(0xffffffffu, interior);
+    const unsigned mb = __ballot_sync(0xffffffffu, boundary);
+    const int lane = threadIdx.x & 31;
+    int bi = 0, bb = 0;
+    if (lane == 0) {
+        if (mi) bi = atomicAdd(cnt + 2 * t, __popc(mi));
+        if (mb) bb = atomicAdd(cnt + 2 * t + 1, __popc(mb));
+    }
+    bi = __shfl_sync(0xffffffffu, bi, 0);
+    bb = __shfl_sync(0xffffffffu, bb, 0);
+    const unsigned lt = (1u << lane) - 1u;
+    if (interior) {
+        const int dst = seg_start[t] + bi + __popc(mi & lt);
+        spos[dst] = p;
+        sx[dst] = p.x; sy[dst] = p.y; sz[dst] = p.z;
+        sidx[dst] = (uint32_t)s;
+    } else if (boundary) {
+        const int dst = seg_end[t] - 1 - (bb + __popc(mb & lt));
+        spos[dst] = p;
+        sx[dst] = p.x; sy[dst] = p.y; sz[dst] = p.z;
+        sidx[dst] = (uint32_t)s;
+    }
+}
+
+// Partition pass, part 2: ghosts into the gap between the two lists, and the class of each block.
+__global__ void __launch_bounds__(256) k_part_fill(int n_slots, int B, const uint8_t *__restrict__ seg_type,
+                                                   const int *__restrict__ seg_start,
+                                                   const int *__restrict__ seg_end, const int *__restrict__ cnt,
+                                                   float4 *__restrict__ spos, float *__restrict__ sx,
+                                                   float *__restrict__ sy, float *__restrict__ sz,
+                                                   uint32_t *__restrict__ sidx, uint8_t *__restrict__ bclass) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_slots) return;
+    const int blk = q / B;
+    const int t = seg_type[blk];
+    const int lo = seg_start[t] + cnt[2 * t];    // first staged index after the interior list
+    const int hi = seg_end[t] - cnt[2 * t + 1];  // first staged index of the boundary list
+    if (q >= lo && q < hi) {
+        spos[q] = make_float4(P3D_GHOST_COORD, P3D_GHOST_COORD, P3D_GHOST_COORD, u2f(P3D_GHOST_ID));
+        sx[q] = P3D_GHOST_COORD; sy[q] = P3D_GHOST_COORD; sz[q] = P3D_GHOST_COORD;
+        sidx[q] = P3D_GHOST_ID;
+    }
+    if (q == blk * B) {
+        const int b0 = q, b1 = q + B;
+        // EMPTY: ghosts only.  INTERIOR: interior entries (and possibly trailing ghosts) but no
+        // boundary entry.  BOUNDARY: holds at least one boundary entry (k_force_bxb walks exactly
+        // the blocks from hi / B on, i.e. those with b1 > hi).
+        uint8_t c;
+        if (b0 >= lo && b1 <= hi) c = P3D_BLK_EMPTY;
+        else if (b1 <= hi) c = P3D_BLK_INTERIOR;
+        else c = P3D_BLK_BOUNDARY;
+        bclass[blk] = c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float2 dup2(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 shfl2(float2 v, int src) {
+    v.x = __shfl_sync(0xffffffffu, v.x, src);
+    v.y = __shfl_sync(0xffffffffu, v.y, src);
+    return v;
+}
+
+// Constants of the branch-free force law, each duplicated into both halves of a packed register.
+// With inv = 1/d:   f(d)/d = min(1/m - inv, 0) + a * max(0, min(c2 - c2*m*inv, c2*inv - c2))
+// which equals src/lib.rs:55-67 divided by d for every d in (0, r) when r >= 1 (the triangle
+// 1 - |2d-1-m|/(1-m) is min(2(d-m), 2(1-d))/(1-m), and dividing by d > 0 commutes with min/max).
+struct PairConsts {
+    float2 c2;     // 2/(1-m)
+    float2 ncm;    // -c2*m
+    float2 nc2;    // -c2
+    float2 im;     // 1/m (or +inf)
+    float2 neg1;   // -1
+    float2 tiny;   // 1e-30: keeps rsqrt finite at d2 == 0 (self pair, coincident particles)
+};
+
+__device__ __forceinline__ PairConsts make_pair_consts(const DevParams &P) {
+    PairConsts c;
+    c.c2 = dup2(P.c2);
+    c.ncm = dup2(-P.c2 * P.m);
+    c.nc2 = dup2(-P.c2);
+    c.im = dup2(P.inv_m);
+    c.neg1 = dup2(-1.0f);
+    c.tiny = dup2(1.0e-30f);
+    return c;
+}
+
+// One i-particle against the lane's two j-particles (one packed register pair per coordinate).
+// The i-position enters as a broadcast scalar operand of FADD2 (SASS: `-R.F32`), so it needs no
+// duplication.  17 packed FP32 instructions + 2 MUFU.RSQ + 6 FMNMX for four ordered interactions.
+// The accumulation order alternates i/j so that consecutive FFMA2 share a source register pair
+// (operand-reuse cache): an FFMA2 that reads three distinct register pairs costs 3 cycles, not 2.
+template <bool RCUT, bool SYM>
+__device__ __forceinline__ void pair_pack(const float2 jx, const float2 jy, const float2 jz, const float nix,
+                                          const float niy, const float niz, const PairConsts &c,
+                                          const float2 aij, const float2 aji, const float r2, float2 &aix,
+                                          float2 &aiy, float2 &aiz, float2 &ajx, float2 &ajy, float2 &ajz) {
+    const float2 dx = __fadd2_rn(jx, dup2(nix));  // other.position - position (src/lib.rs:211-212, offset 0)
+    const float2 dy = __fadd2_rn(jy, dup2(niy));
+    const float2 dz = __fadd2_rn(jz, dup2(niz));
+    float2 d2 = __ffma2_rn(dx, dx, c.tiny);
+    d2 = __ffma2_rn(dy, dy, d2);
+    d2 = __ffma2_rn(dz, dz, d2);
+    const float2 inv = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
+    const float2 p1 = __ffma2_rn(inv, c.ncm, c.c2);   // c2 * (1 - m/d)
+    const float2 p2 = __ffma2_rn(inv, c.c2, c.nc2);   // c2 * (1/d - 1)
+    float2 ti = make_float2(fmaxf(fminf(p1.x, p2.x), 0.0f), fmaxf(fminf(p1.y, p2.y), 0.0f));
+    float2 rs = __ffma2_rn(inv, c.neg1, c.im);        // 1/m - 1/d
+    rs = make_float2(fminf(rs.x, 0.0f), fminf(rs.y, 0.0f));
+    if (RCUT) {  // r < 1: src/lib.rs:216-220 cuts inside the force range
+        if (!(d2.x < r2)) { ti.x = 0.0f; rs.x = 0.0f; }
+        if (!(d2.y < r2)) { ti.y = 0.0f; rs.y = 0.0f; }
+    }
+    const float2 sij = __ffma2_rn(aij, ti, rs);       // f(d; A[i][j]) / d
+    if (SYM) {
+        const float2 sji = __ffma2_rn(aji, ti, rs);   // f(d; A[j][i]) / d
+        aix = __ffma2_rn(dx, sij, aix);               // acc += rel / d * f  (src/lib.rs:231)
+        ajx = __ffma2_rn(dx, sji, ajx);               // negated when flushed: rel_ji = -rel_ij
+        ajy = __ffma2_rn(dy, sji, ajy);
+        aiy = __ffma2_rn(dy, sij, aiy);
+        aiz = __ffma2_rn(dz, sij, aiz);
+        ajz = __ffma2_rn(dz, sji, ajz);
+    } else {
+        aix = __ffma2_rn(dx, sij, aix);
+        aiy = __ffma2_rn(dy, sij, aiy);
+        aiz = __ffma2_rn(dz, sij, aiz);
+    }
+}
+
+__device__ __forceinline__ void atomic_add_f3(float4 *dst, float x, float y, float z) {
+    // sm_90+ vector atomic: one 16-byte RED per particle
+    atomicAdd(dst, make_float4(x, y, z, 0.0f));
+}
+
+// K1 (fast): symmetric block-pair force pass.  grid.x = n_rows * splits, block = NW warps.
+// Row a (row_begin + k*row_stride: the multi-GPU shard takes every world-th row) owns the block
+// pairs {a, a+o mod M}, o in [0, M/2]; the warps of the `splits` CTAs of a row interleave over o.
+template <int R, bool RCUT>
+__global__ void __launch_bounds__(128, 4)
+k_force_pair(const float *__restrict__ sx, const float *__restrict__ sy, const float *__restrict__ sz,
+             const uint32_t *__restrict__ sidx,
+             const uint8_t *__restrict__ bclass, const uint8_t *__restrict__ btype, int M, int row_begin,
+             int row_stride, int splits, float4 *__restrict__ frc, DevParams P,
+             const float *__restrict__ matrix, const int *__restrict__ flags) {
+    if (flags[0] != 0) return;  // some particle is outside the box: the reference-order kernel runs instead
+    constexpr int B = 32 * R;
+    constexpr int ROUNDS = B / 64;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+    const int row = row_begin + (blockIdx.x / splits) * row_stride;
+    const int split = blockIdx.x % splits;
+    if (row >= M) return;
+    const uint8_t ca = bclass[row];
+    if (ca == P3D_BLK_EMPTY) return;
+    const int ta = btype[row];
+    const PairConsts c = make_pair_consts(P);
+
+    float nix[R], niy[R], niz[R];
+    float2 aix[R], aiy[R], aiz[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int s = row * B + r * 32 + lane;
+        nix[r] = -sx[s]; niy[r] = -sy[s]; niz[r] = -sz[s];
+        aix[r] = aiy[r] = aiz[r] = make_float2(0.f, 0.f);
+    }
+
+    const int omax = M / 2;  // M even: offset M/2 is shared by rows a and a+M/2; the lower row takes it
+    const int next = (lane + 1) & 31;
+    for (int o = split * nw + warp; o <= omax; o += splits * nw) {
+        if (((M & 1) == 0) && o == omax && row >= omax && o != 0) continue;
+        int b = row + o;
+        if (b >= M) b -= M;
+        const uint8_t cb = bclass[b];
+        if (cb == P3D_BLK_EMPTY) continue;
+        if (ca == P3D_BLK_BOUNDARY && cb == P3D_BLK_BOUNDARY) continue;  // -> k_force_bxb
+        const int tb = btype[b];
+        const float2 aij = dup2(matrix[ta * P.T + tb]);
+        const float2 aji = dup2(matrix[tb * P.T + ta]);
+        const bool diag = (o == 0);
+#pragma unroll 1
+        for (int round = 0; round < ROUNDS; ++round) {
+            const int base = b * B + round * 64 + 2 * lane;  // two consecutive j per lane: native register pairs
+            float2 jx = *reinterpret_cast<const float2 *>(sx + base);
+            float2 jy = *reinterpret_cast<const float2 *>(sy + base);
+            float2 jz = *reinterpret_cast<const float2 *>(sz + base);
+            float2 ajx = make_float2(0.f, 0.f), ajy = ajx, ajz = ajx;
+#pragma unroll 1
+            for (int step = 0; step < 32; ++step) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    pair_pack<RCUT, true>(jx, jy, jz, nix[r], niy[r], niz[r], c, aij, aji, P.r2, aix[r], aiy[r],
+                                          aiz[r], ajx, ajy, ajz);
+                jx = shfl2(jx, next); jy = shfl2(jy, next); jz = shfl2(jz, next);
+                ajx = shfl2(ajx, next); ajy = shfl2(ajy, next); ajz = shfl2(ajz, next);
+            }
+            // 32 rotations bring every j (and its accumulator) back to its home lane
+            if (!diag) {
+                const uint32_t s0 = sidx[base], s1 = sidx[base + 1];
+                if (s0 != P3D_GHOST_ID) atomic_add_f3(frc + s0, -ajx.x, -ajy.x, -ajz.x);
+                if (s1 != P3D_GHOST_ID) atomic_add_f3(frc + s1, -ajx.y, -ajy.y, -ajz.y);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t s = sidx[row * B + r * 32 + lane];
+        if (s != P3D_GHOST_ID)
+            atomic_add_f3(frc + s, aix[r].x + aix[r].y, aiy[r].x + aiy[r].y, aiz[r].x + aiz[r].y);
+    }
+}
+
+// K1 (boundary x boundary): ordered pairs between BOUNDARY-class blocks, with the reference's exact
+// image arithmetic (three candidates per axis, rounding of position + offset, exact sqrt and divides).
+// One thread per i; the boundary blocks of each type are the tail of that type's region.
+template <int B>
+__global__ void __launch_bounds__(B) k_force_bxb(const float4 *__restrict__ spos, const uint32_t *__restrict__ sidx,
+                                                 const uint8_t *__restrict__ bclass, int M, int row_begin,
+                                                 int row_stride, const int *__restrict__ seg_start,
+                                                 const int *__restrict__ seg_end, const int *__restrict__ cnt,
+                                                 float4 *__restrict__ frc, DevParams P,
+                                                 const float *__restrict__ matrix, const int *__restrict__ flags) {
+    if (flags[0] != 0) return;
+    const int row = row_begin + blockIdx.x * row_stride;
+    if (row >= M || bclass[row] != P3D_BLK_BOUNDARY) return;
+    extern __shared__ float4 sm_dyn[];
+    float4 *tile = sm_dyn;
+    float *smat = reinterpret_cast<float *>(sm_dyn + B);
+    for (int k = threadIdx.x; k < P.T * P.T; k += B) smat[k] = matrix[k];
+
+    const float4 pi = spos[row * B + threadIdx.x];
+    const uint32_t idi = f2u(pi.w);
+    const bool live = idi != P3D_GHOST_ID;
+    const float pxm = __fadd_rn(pi.x, -P.W), pxp = __fadd_rn(pi.x, P.W);
+    const float pym = __fadd_rn(pi.y, -P.W), pyp = __fadd_rn(pi.y, P.W);
+    const float pzm = __fadd_rn(pi.z, -P.W), pzp = __fadd_rn(pi.z, P.W);
+    const uint32_t mrow = live ? idi * (uint32_t)P.T : 0u;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int t = 0; t < P.T; ++t) {
+        const int hi = seg_end[t] - cnt[2 * t + 1];  // first boundary entry of type t
+        const int b_first = hi / B;                  // the block holding it (BOUNDARY or EMPTY if none)
+        const int b_last = seg_end[t] / B;
+        for (int b = b_first; b < b_last; ++b) {
+            if (bclass[b] != P3D_BLK_BOUNDARY) continue;
+            __syncthreads();
+            tile[threadIdx.x] = spos[b * B + threadIdx.x];
+            __syncthreads();
+            if (!live) continue;
+#pragma unroll 4
+            for (int k = 0; k < B; ++k) {
+                const float4 q = tile[k];
+                const float rx = nearest_image3(q.x, pi.x, pxm, pxp);
+                const float ry = nearest_image3(q.y, pi.y, pym, pyp);
+                const float rz = nearest_image3(q.z, pi.z, pzm, pzp);
+                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
+                if (d2 > 0.0f && d2 < P.r2) {
+                    const float d = __fsqrt_rn(d2);
+                    const float a = smat[mrow + f2u(q.w)];
+                    const float f = ref_calculate_force(P.m, d, a);
+                    ax = __fadd_rn(ax, __fmul_rn(__fdiv_rn(rx, d), f));
+                    ay = __fadd_rn(ay, __fmul_rn(__fdiv_rn(ry, d), f));
+                    az = __fadd_rn(az, __fmul_rn(__fdiv_rn(rz, d), f));
+                }
+            }
+        }
+    }
+    if (live) atomic_add_f3(frc + sidx[row * B + threadIdx.x], ax, ay, az);
+}

@@ -1,0 +1,154 @@
+/* p3d.h — C ABI of the B200-native step engine for the `particle_3d` crate.
+ *
+ * The reference (navpreett/3D-Particle-Simulation-) has NO FFI/plugin layer: its boundary is
+ * the Rust public API  `Particle` (src/lib.rs:12-17), `Particles` (src/lib.rs:20-33) and
+ * `Particles::update(&mut self, ts: f32) -> Vec<Particle>` (src/lib.rs:130).  This header is
+ * the boundary a `build.rs` + `extern "C"` shim inside that crate would bind (the shim is shown
+ * in INTEGRATION.md).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * There is no CPU fallback: every compute entry point returns P3D_ERR_NO_DEVICE / P3D_ERR_CUDA
+ * when the GPU path cannot run.
+ */
+#ifndef P3D_H
+#define P3D_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P3D_ABI_VERSION 1
+
+/* ---- error codes (the Rust shim turns non-zero into the panic the reference would raise) ---- */
+#define P3D_OK 0
+#define P3D_ERR_WORLD_TOO_SMALL 1 /* replaces assert!(world_size >= 2*radius), src/lib.rs:132 */
+#define P3D_ERR_BAD_ID 2          /* replaces the slice-index panic at src/lib.rs:225-228 (id >= id_count) */
+#define P3D_ERR_CUDA 3            /* any CUDA runtime failure; text in p3d_last_error() */
+#define P3D_ERR_INVALID 4         /* null pointer, n mismatch, unsupported id_count, bad option */
+#define P3D_ERR_NO_DEVICE 5       /* no CUDA device / not sm_100 */
+
+#define P3D_MAX_TYPES 64 /* id_count limit of this engine (reference: unbounded u32) */
+
+/* ---- data crossing the boundary ---- */
+
+/* Replaces `struct Particle` (src/lib.rs:12-17): position, velocity (cgmath::Vector3<f32>), id.
+ * 28 bytes, align 4.  The Rust struct is not #[repr(C)]; the shim adds it. */
+typedef struct p3d_particle {
+    float px, py, pz;
+    float vx, vy, vz;
+    uint32_t id;
+} p3d_particle;
+
+/* Replaces the scalar fields of `struct Particles` (src/lib.rs:20-33) read by update().
+ * Passed on EVERY call: the caller may change any field between steps (src/bin/main.rs:263-359). */
+typedef struct p3d_params {
+    float world_size;              /* src/lib.rs:21 */
+    float coefficient;             /* :27 drag */
+    float interaction_force;       /* :28 */
+    float min_pull_ratio;          /* :29 */
+    float particle_effect_radius;  /* :30 */
+    float accel[3];                /* :32 acceleration */
+    uint32_t walls;                /* :31 bool */
+    uint32_t id_count;             /* :24 */
+    const float *attraction_matrix;/* :25 id_count*id_count floats, [self_id*id_count + other_id] */
+} p3d_params;
+
+typedef struct p3d_engine p3d_engine; /* opaque; owns device buffers, stream, events */
+
+/* ---- engine lifetime ---- */
+int p3d_abi_version(void);
+/* Creates an engine on CUDA device `device`.  Not thread-safe: one caller at a time per handle
+ * (mirrors `&mut self` at src/lib.rs:130). */
+int p3d_create(int device, p3d_engine **out);
+void p3d_destroy(p3d_engine *eng);
+/* Message for the last non-zero return on this thread. */
+const char *p3d_last_error(void);
+
+/* ---- the drop-in call: replaces Particles::update (src/lib.rs:130-272) ----
+ * in/out are HOST arrays of n particles (may alias).  After the call out[i] is the updated
+ * particle i (same index order, src/lib.rs:171-173,268); `in` is the state the reference leaves
+ * in `past_particles` (src/lib.rs:167).  Synchronous.  n may differ from the previous call. */
+int p3d_update(p3d_engine *eng, const p3d_params *prm, float ts,
+               const p3d_particle *in, p3d_particle *out, size_t n);
+
+/* ---- device-resident stepping (benches, headless runs; state stays in HBM between steps) ---- */
+int p3d_upload(p3d_engine *eng, const p3d_particle *in, size_t n, uint32_t id_count);
+/* n_steps x update(ts) without host round trips; asynchronous on the engine stream. */
+int p3d_step(p3d_engine *eng, const p3d_params *prm, float ts, int n_steps);
+int p3d_download(p3d_engine *eng, p3d_particle *out, size_t n);
+int p3d_sync(p3d_engine *eng);
+/* total_force of src/lib.rs:177-243 from the most recent step, in particle index order (n*3). */
+int p3d_download_forces(p3d_engine *eng, float *out_xyz, size_t n);
+/* out[0]=sum 0.5*|v|^2, out[1..3]=sum v, out[4]=max |v|^2, out[5]=count, out[6]=sum |p|^2, out[7]=0 */
+int p3d_diagnostics(p3d_engine *eng, double out[8]);
+
+/* ---- options ---- */
+enum p3d_option {
+    P3D_OPT_FORCE_KERNEL = 0, /* see p3d_force_kernel */
+    P3D_OPT_TIMING = 1,       /* 1: record CUDA events around each kernel of a step */
+    P3D_OPT_GRAPH = 2,        /* 1: replay p3d_step through a CUDA graph */
+    P3D_OPT_BLOCK_SORT = 3,   /* 1: re-partition interior/boundary blocks every step (fast path) */
+    P3D_OPT_BLOCK_SIZE = 4    /* particles per block of the pair kernel: 128 (R=4) or 256 (R=8); applies at the next upload */
+};
+enum p3d_force_kernel {
+    P3D_FORCE_AUTO = 0,      /* PAIR for n >= 4096, else REFERENCE_ORDER */
+    P3D_FORCE_REFERENCE_ORDER = 1, /* one thread per particle, exact sqrt/div, all three images per axis */
+    P3D_FORCE_PAIR = 2       /* symmetric block-pair kernel, packed FP32x2, rsqrt */
+};
+int p3d_set_option(p3d_engine *eng, int option, int value);
+int p3d_get_option(p3d_engine *eng, int option, int *value);
+
+/* Per-kernel device times of the most recent p3d_step/p3d_update (needs P3D_OPT_TIMING=1),
+ * milliseconds summed over the steps of that call: [0]=force [1]=integrate [2]=pack(upload side)
+ * [3]=unpack(download side) [4]=re-partition [5]=h2d copy [6]=d2h copy [7]=whole call. */
+int p3d_get_timing(p3d_engine *eng, float ms[8]);
+/* Launch counters since creation: [0]=kernels launched, [1]=force kernels, [2]=integrate kernels. */
+int p3d_get_counters(p3d_engine *eng, uint64_t out[4]);
+
+/* ---- plumbing for one-process-per-GPU drivers (torch.distributed owns the collective) ---- */
+/* Run every subsequent launch on this cudaStream_t (e.g. torch's current stream); NULL = own stream. */
+int p3d_set_stream(p3d_engine *eng, void *cuda_stream);
+enum p3d_buffer {
+    P3D_BUF_POS = 0,      /* float4 {x,y,z,id bits} per slot, current positions */
+    P3D_BUF_POS_NEXT = 1, /* float4 per slot, written by integrate */
+    P3D_BUF_VEL = 2,      /* float4 {vx,vy,vz,0} per slot */
+    P3D_BUF_FORCE = 3     /* float4 {fx,fy,fz,0} per slot */
+};
+/* Device pointer + element count (slots, >= n because type segments are padded). */
+int p3d_device_buffer(p3d_engine *eng, int which, void **dev_ptr, size_t *n_slots);
+/* Shard = the slot range this rank integrates and, for the force pass, its share of block rows.
+ * world==1 restores single-GPU behaviour. */
+int p3d_set_shard(p3d_engine *eng, int rank, int world);
+int p3d_shard_range(p3d_engine *eng, size_t *slot_begin, size_t *slot_end);
+/* One step split at the collectives a multi-GPU driver inserts:
+ *   p3d_shard_force     -> partial forces (this rank's block rows) into P3D_BUF_FORCE
+ *   [driver: sum-reduce P3D_BUF_FORCE across ranks when the PAIR kernel is used]
+ *   p3d_shard_integrate -> integrates [slot_begin,slot_end) into P3D_BUF_POS_NEXT / P3D_BUF_VEL
+ *   [driver: all-gather P3D_BUF_POS_NEXT across ranks]
+ *   p3d_shard_commit    -> swaps POS/POS_NEXT */
+int p3d_shard_force(p3d_engine *eng, const p3d_params *prm);
+int p3d_shard_integrate(p3d_engine *eng, const p3d_params *prm, float ts);
+int p3d_shard_commit(p3d_engine *eng);
+
+/* ---- FP32-pipe microbenchmarks: make the roofline denominator defensible ----
+ * kind 0: dependent-chain-free scalar FFMA; 1: packed FFMA2; 2: the pair kernel's instruction mix
+ * (17 FFMA2/FADD2 : 2 MUFU.RSQ : 6 FMNMX); 3: FFMA2 with the pair kernel's shuffle rate (12 SHFL per 68 FFMA2).
+ * out[0] = FP32 lane-FMAs per second (an FFMA2 counts 2 per lane), out[1] = kernel ms,
+ * out[2] = SM count, out[3] = max SM clock in MHz as reported by the driver. */
+int p3d_microbench(int device, int kind, int iters, double out[4]);
+
+/* ---- seeded scenes (host only; restates the binary-private generator, src/bin/main.rs:60-87,
+ *      and the default scene constants, src/bin/main.rs:123-148) ---- */
+/* Fills prm with the default scene; matrix25 receives the 5x5 default matrix and prm points at it. */
+void p3d_scene_default_params(p3d_params *prm, float matrix25[25]);
+/* Uniform positions in [-W/2, W/2]^3, zero velocity, ids uniform in 0..id_count (splitmix64, seeded). */
+void p3d_scene_uniform(uint64_t seed, size_t n, float world_size, uint32_t id_count, p3d_particle *out);
+/* Plummer-like cloud: radius from the Plummer CDF with scale a, isotropic, rejected outside the box. */
+void p3d_scene_plummer(uint64_t seed, size_t n, float world_size, float scale_a, uint32_t id_count,
+                       p3d_particle *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P3D_H */

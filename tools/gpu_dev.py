@@ -1,0 +1,137 @@
+"""Developer GPU probe: parity vs oracle + kernel timings + FP32 microbench.  Not part of the product."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "3d-particle-simulation-_b200"))
+sys.path.insert(0, ROOT)
+import particle_3d as p3
+from particle_3d import _abi
+from oracle import oracle as O
+
+
+def parity(n, W, kernel, steps=1, seed=42, plummer=False, block=128, **over):
+    prm = p3.default_params_dict()
+    prm["world_size"] = W
+    prm.update(over)
+    parts = p3.generate_plummer(W, n, W / 6, seed) if plummer else p3.generate_particles(W, n, seed)
+    eng = p3.Engine(0)
+    eng.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+    eng.set_option(_abi.OPT_BLOCK_SIZE, block)
+    P = p3.Engine.make_params(**prm)
+    cur = parts.copy()
+    ref = parts.copy()
+    for _ in range(steps):
+        cur = eng.update(P, 1 / 60, cur)
+        ref = O.update(prm, 1 / 60, ref, mode=O.IDEAL)["out"]
+    v = np.stack([cur["vx"], cur["vy"], cur["vz"]], 1).astype(np.float64)
+    vr = np.stack([ref["vx"], ref["vy"], ref["vz"]], 1).astype(np.float64)
+    p = np.stack([cur["px"], cur["py"], cur["pz"]], 1).astype(np.float64)
+    pr = np.stack([ref["px"], ref["py"], ref["pz"]], 1).astype(np.float64)
+    vrms = np.sqrt((vr ** 2).sum(1).mean())
+    dv = np.linalg.norm(v - vr, axis=1) / np.maximum(np.linalg.norm(vr, axis=1), vrms)
+    dp = np.linalg.norm(p - pr, axis=1) / np.maximum(np.linalg.norm(pr, axis=1), W / 2)
+    print(f"parity n={n} W={W} kernel={kernel} steps={steps} {over}: max dv={dv.max():.3e} (n>1e-5: {(dv>1e-5).sum()}) "
+          f"max dp={dp.max():.3e} ids_ok={np.array_equal(cur['id'], ref['id'])}", flush=True)
+    eng.close()
+
+
+class Clocks:
+    """Samples nvidia-smi SM clock / power / throttle reasons while a region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active"
+
+    def __enter__(self):
+        import subprocess
+        self.p = subprocess.Popen(["nvidia-smi", "-i", "0", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                  stdout=subprocess.PIPE, text=True)
+        return self
+
+    def __exit__(self, *a):
+        self.p.terminate()
+        out = self.p.communicate()[0].strip().splitlines()
+        rows = [r.split(", ") for r in out if r]
+        clk = sorted(float(r[0]) for r in rows)
+        pw = [float(r[2]) for r in rows]
+        self.summary = dict(samples=len(rows), sm_mhz_median=clk[len(clk) // 2] if clk else None,
+                            sm_mhz_min=clk[0] if clk else None, sm_max=float(rows[0][1]) if rows else None,
+                            power_max=max(pw) if pw else None, reasons=sorted(set(r[3] for r in rows)))
+
+
+def timing(n, W, kernel, steps=3, plummer=False, block=128):
+    prm = p3.default_params_dict()
+    prm["world_size"] = W
+    parts = p3.generate_plummer(W, n, W / 6, 42) if plummer else p3.generate_particles(W, n, 42)
+    eng = p3.Engine(0)
+    eng.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+    eng.set_option(_abi.OPT_TIMING, 1)
+    eng.set_option(_abi.OPT_BLOCK_SIZE, block)
+    P = p3.Engine.make_params(**prm)
+    eng.upload(parts, 5)
+    eng.step(P, 1 / 60, 1)
+    eng.sync()
+    with Clocks() as ck:
+        t0 = time.time()
+        eng.step(P, 1 / 60, steps)
+        eng.sync()
+        wall = (time.time() - t0) / steps
+    t = eng.timing()
+    f_ms = t["force"] / steps
+    i_ms = t["integrate"] / steps
+    pairs = float(n) * n
+    print(f"timing n={n} kernel={kernel}: force {f_ms:.3f} ms  integrate {i_ms*1e3:.1f} us  wall/step {wall*1e3:.3f} ms  "
+          f"{pairs/f_ms/1e9:.2f} T interactions/s  = {pairs*20/(f_ms*1e-3)/74.5e12*100:.1f}% of 74.5 TF  "
+          f"integrate {80*n/i_ms/1e6:.0f} GB/s  B={block}  clocks={ck.summary}", flush=True)
+    eng.close()
+
+
+def micro():
+    L = _abi.load()
+    for kind, name in ((0, "FFMA"), (1, "FFMA2"), (2, "pair-mix"), (3, "FFMA2+SHFL")):
+        out = (C.c_double * 4)()
+        rc = L.p3d_microbench(0, kind, 2000, out)
+        print(f"micro {name}: rc={rc} {out[0]/1e12:.2f} T lane-FMA/s  ({out[0]*2/1e12:.1f} TFLOP/s)  {out[1]:.2f} ms  "
+              f"sms={int(out[2])} clk={out[3]:.0f} MHz  -> per SM per clk @max: {out[0]/out[2]/(out[3]*1e6):.1f}", flush=True)
+
+
+def micro2():
+    L = _abi.load()
+    names = {4: "6 FMNMX", 5: "2 MUFU.RSQ", 6: "3 SHFL", 7: "17 FFMA2 + 6 FMNMX", 8: "17 FFMA2 + 2 MUFU",
+             9: "34 FFMA + 6 FMNMX + 2 MUFU", 10: "17 FFMA2 + 6 FMNMX + 2 MUFU", 11: "17 FFMA2 + 6 FMNMX + 2 MUFU + 3 SHFL",
+             12: "17 FFMA2"}
+    for kind in sorted(names):
+        out = (C.c_double * 4)()
+        rc = L.p3d_microbench(0, kind, 1000, out)
+        warp_bodies_per_s = out[0] / 32
+        cyc = out[3] * 1e6 * out[2] * 4 / warp_bodies_per_s
+        print(f"micro2 [{names[kind]}]: rc={rc} {out[1]:.2f} ms -> {cyc:.1f} SMSP-cycles per warp-body (at max clock)", flush=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["parity", "timing", "micro"]
+    if "micro" in what:
+        micro()
+        micro2()
+    if "parity" in what:
+        parity(1000, 10.0, _abi.FORCE_REFERENCE_ORDER)
+        parity(1000, 10.0, _abi.FORCE_PAIR)
+        parity(1000, 10.0, _abi.FORCE_REFERENCE_ORDER, steps=10)
+        parity(16384, 25.4, _abi.FORCE_PAIR)
+        parity(16384, 25.4, _abi.FORCE_PAIR, block=256)
+        parity(16384, 25.4, _abi.FORCE_REFERENCE_ORDER)
+        parity(16384, 25.4, _abi.FORCE_PAIR, walls=True, acceleration=(0.0, -1.0, 0.0))
+        parity(16384, 25.4, _abi.FORCE_PAIR, particle_effect_radius=0.8)
+        parity(20000, 64.0, _abi.FORCE_PAIR, plummer=True)
+    if "timing" in what:
+        timing(1000, 10.0, _abi.FORCE_REFERENCE_ORDER, steps=20)
+        timing(16384, 25.4, _abi.FORCE_REFERENCE_ORDER, steps=5)
+        timing(16384, 25.4, _abi.FORCE_PAIR, steps=20)
+        timing(16384, 25.4, _abi.FORCE_PAIR, steps=20, block=256)
+        timing(262144, 64.0, _abi.FORCE_PAIR, steps=3)
+        timing(262144, 64.0, _abi.FORCE_PAIR, steps=3, block=256)
+        timing(1048576, 101.6, _abi.FORCE_PAIR, steps=4)
+        timing(1048576, 101.6, _abi.FORCE_PAIR, steps=4, block=256)
