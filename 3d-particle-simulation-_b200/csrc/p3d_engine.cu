@@ -42,6 +42,7 @@ int fail(int code, const char *fmt, ...) {
     } while (0)
 
 constexpr int kMaxTimedSteps = 512;
+constexpr int kEv = 5;  // events per timed step
 constexpr int kRefTile = 128;       // threads per CTA of the reference-order kernel
 constexpr int kPairAutoMin = 4096;  // P3D_FORCE_AUTO switches to the pair kernel from this n
 
@@ -109,11 +110,12 @@ struct p3d_engine {
     int rank = 0, world = 1;
 
     // timing
-    std::vector<cudaEvent_t> ev;  // 3 per timed step: before force, after force, after integrate
+    std::vector<cudaEvent_t> ev;  // kEv per timed step: start, after partition, after pair, after force, after integrate
     int timed_steps = 0;
     cudaEvent_t ev_call[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool call_timed = false;
-    float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float last_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t *step_ev = nullptr;  // events of the step being recorded (null: untimed)
     uint64_t counters[4] = {0, 0, 0, 0};
 };
 
@@ -186,6 +188,11 @@ int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T) {
         e->seg_end_h[t] = (int)at;
     }
     if (at == 0) at = B;  // keep one (ghost) block so kernels always have a valid grid
+    {   // equal shards for the multi-GPU all-gather: the last type's region absorbs the padding blocks
+        const size_t unit = (size_t)B * (size_t)e->world;
+        at = (at + unit - 1) / unit * unit;
+        e->seg_end_h[T - 1] = (int)at;
+    }
     e->n_slots = (int)at;
     e->M = e->n_slots / B;
     e->n = n;
@@ -274,6 +281,10 @@ int launch_force(p3d_engine *e, const DevParams &P) {
     const float4 *pos = e->pos[e->cur].p;
     if (kind == P3D_FORCE_REFERENCE_ORDER) {
         CU(cudaMemsetAsync(flag_next, 0, sizeof(int), st));
+        if (e->step_ev) {
+            CU(cudaEventRecord(e->step_ev[1], st));
+            CU(cudaEventRecord(e->step_ev[2], st));
+        }
         // shard: contiguous slot range
         const int per = ((e->M + e->world - 1) / e->world) * e->B;
         const int i0 = std::min(ns, e->rank * per), i1 = std::min(ns, i0 + per);
@@ -298,6 +309,7 @@ int launch_force(p3d_engine *e, const DevParams &P) {
                                                  e->spos.p, e->sx.p, e->sy.p, e->sz.p, e->sidx.p, e->bclass.p);
     CU(cudaMemsetAsync(e->frc.p, 0, (size_t)ns * sizeof(float4), st));
     e->counters[0] += 2;
+    if (e->step_ev) CU(cudaEventRecord(e->step_ev[1], st));
 
     const int M = e->M;
     const int rows = (M - e->rank + e->world - 1) / e->world;  // rows rank, rank+world, ...
@@ -309,34 +321,25 @@ int launch_force(p3d_engine *e, const DevParams &P) {
                                               std::max<long long>(1, (8LL * 4 * e->sm_count + rows - 1) / rows));
         if (splits < 1) splits = 1;
         const dim3 grid((unsigned)rows * (unsigned)splits);
+        const float *sx = e->sx.p, *sy = e->sy.p, *sz = e->sz.p;
+#define P3D_PAIR_ARGS sx, sy, sz, e->sidx.p, e->bclass.p, e->seg_type.p, M, e->rank, e->world, splits, e->frc.p, P, e->matrix.p, flag_cur
         if (B == 128) {
-            if (P.rcut)
-                k_force_pair<4, true><<<grid, nw * 32, 0, st>>>(e->sx.p, e->sy.p, e->sz.p, e->sidx.p, e->bclass.p, e->seg_type.p, M,
-                                                                e->rank, e->world, splits, e->frc.p, P,
-                                                                e->matrix.p, flag_cur);
-            else
-                k_force_pair<4, false><<<grid, nw * 32, 0, st>>>(e->sx.p, e->sy.p, e->sz.p, e->sidx.p, e->bclass.p, e->seg_type.p, M,
-                                                                 e->rank, e->world, splits, e->frc.p, P,
-                                                                 e->matrix.p, flag_cur);
-            k_force_bxb<128><<<rows, 128, ref_smem(128, P.T), st>>>(e->spos.p, e->sidx.p, e->bclass.p, M, e->rank,
-                                                                    e->world, e->seg_start.p, e->seg_end.p,
-                                                                    e->cnt.p, e->frc.p, P, e->matrix.p, flag_cur);
+            if (P.rcut) k_force_pair<4, true><<<grid, nw * 32, 0, st>>>(P3D_PAIR_ARGS);
+            else        k_force_pair<4, false><<<grid, nw * 32, 0, st>>>(P3D_PAIR_ARGS);
         } else {
-            if (P.rcut)
-                k_force_pair<8, true><<<grid, nw * 32, 0, st>>>(e->sx.p, e->sy.p, e->sz.p, e->sidx.p, e->bclass.p, e->seg_type.p, M,
-                                                                e->rank, e->world, splits, e->frc.p, P,
-                                                                e->matrix.p, flag_cur);
-            else
-                k_force_pair<8, false><<<grid, nw * 32, 0, st>>>(e->sx.p, e->sy.p, e->sz.p, e->sidx.p, e->bclass.p, e->seg_type.p, M,
-                                                                 e->rank, e->world, splits, e->frc.p, P,
-                                                                 e->matrix.p, flag_cur);
-            k_force_bxb<256><<<rows, 256, ref_smem(256, P.T), st>>>(e->spos.p, e->sidx.p, e->bclass.p, M, e->rank,
-                                                                    e->world, e->seg_start.p, e->seg_end.p,
-                                                                    e->cnt.p, e->frc.p, P, e->matrix.p, flag_cur);
+            if (P.rcut) k_force_pair<8, true><<<grid, nw * 32, 0, st>>>(P3D_PAIR_ARGS);
+            else        k_force_pair<8, false><<<grid, nw * 32, 0, st>>>(P3D_PAIR_ARGS);
         }
+#undef P3D_PAIR_ARGS
+        if (e->step_ev) CU(cudaEventRecord(e->step_ev[2], st));
+#define P3D_BXB_ARGS e->spos.p, e->sidx.p, e->bclass.p, M, e->rank, e->world, e->seg_start.p, e->seg_end.p, e->cnt.p, e->frc.p, P, e->matrix.p, flag_cur
+        if (B == 128) k_force_bxb<128><<<rows, 128, ref_smem(128, P.T), st>>>(P3D_BXB_ARGS);
+        else          k_force_bxb<256><<<rows, 256, ref_smem(256, P.T), st>>>(P3D_BXB_ARGS);
+#undef P3D_BXB_ARGS
         e->counters[0] += 2;
         e->counters[1] += 2;
     }
+    else if (e->step_ev) CU(cudaEventRecord(e->step_ev[2], st));
     // out-of-box inputs (flag set): the reference-order kernel takes the whole step instead
     {
         const int per = ((M + e->world - 1) / e->world) * B;
@@ -378,7 +381,7 @@ int upload_matrix(p3d_engine *e, const p3d_params *prm) {
 }
 
 int ensure_events(p3d_engine *e, int steps) {
-    const size_t need = (size_t)std::min(steps, kMaxTimedSteps) * 3;
+    const size_t need = (size_t)std::min(steps, kMaxTimedSteps) * kEv;
     while (e->ev.size() < need) {
         cudaEvent_t x;
         CU(cudaEventCreate(&x));
@@ -406,14 +409,16 @@ int run_steps(p3d_engine *e, const p3d_params *prm, const DevParams &P, float ts
     if (e->opt_timing && (rc = ensure_events(e, n_steps))) return rc;
     for (int s = 0; s < n_steps; ++s) {
         const bool timed = e->opt_timing && s < kMaxTimedSteps;
-        if (timed) CU(cudaEventRecord(e->ev[3 * s], e->stream));
-        if ((rc = launch_force(e, P))) return rc;
-        if (timed) CU(cudaEventRecord(e->ev[3 * s + 1], e->stream));
-        if ((rc = launch_integrate(e, P, ts))) return rc;
+        e->step_ev = timed ? &e->ev[(size_t)kEv * s] : nullptr;
+        if (timed) CU(cudaEventRecord(e->step_ev[0], e->stream));
+        if ((rc = launch_force(e, P))) { e->step_ev = nullptr; return rc; }
+        if (timed) CU(cudaEventRecord(e->step_ev[3], e->stream));
+        if ((rc = launch_integrate(e, P, ts))) { e->step_ev = nullptr; return rc; }
         if (timed) {
-            CU(cudaEventRecord(e->ev[3 * s + 2], e->stream));
+            CU(cudaEventRecord(e->step_ev[4], e->stream));
             e->timed_steps = s + 1;
         }
+        e->step_ev = nullptr;
         e->cur ^= 1;
         e->parity ^= 1;
     }
@@ -618,21 +623,25 @@ int p3d_diagnostics(p3d_engine *e, double out[8]) {
     return P3D_OK;
 }
 
-int p3d_get_timing(p3d_engine *e, float ms[8]) {
+int p3d_get_timing(p3d_engine *e, float ms[12]) {
     if (!e || !ms) return fail(P3D_ERR_INVALID, "null argument");
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream));
-    float f = 0.f, g = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};  // partition, pair, rest of force, integrate
     for (int s = 0; s < e->timed_steps; ++s) {
-        float a = 0.f, b = 0.f;
-        CU(cudaEventElapsedTime(&a, e->ev[3 * s], e->ev[3 * s + 1]));
-        CU(cudaEventElapsedTime(&b, e->ev[3 * s + 1], e->ev[3 * s + 2]));
-        f += a;
-        g += b;
+        for (int k = 0; k < 4; ++k) {
+            float a = 0.f;
+            CU(cudaEventElapsedTime(&a, e->ev[(size_t)kEv * s + k], e->ev[(size_t)kEv * s + k + 1]));
+            acc[k] += a;
+        }
     }
-    e->last_ms[0] = f;
-    e->last_ms[1] = g;
-    e->last_ms[7] = f + g;
+    e->last_ms[0] = acc[0] + acc[1] + acc[2];
+    e->last_ms[1] = acc[3];
+    e->last_ms[4] = acc[0];
+    e->last_ms[7] = acc[0] + acc[1] + acc[2] + acc[3];
+    e->last_ms[8] = acc[1];
+    e->last_ms[9] = acc[2];
+    e->last_ms[10] = (float)e->timed_steps;
     std::memcpy(ms, e->last_ms, sizeof(e->last_ms));
     return P3D_OK;
 }

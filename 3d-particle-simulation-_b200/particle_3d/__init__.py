@@ -123,9 +123,9 @@ class Engine:
         return v.value
 
     def timing(self) -> dict:
-        ms = (C.c_float * 8)()
+        ms = (C.c_float * 12)()
         _abi.check(self._lib.p3d_get_timing(self._h, ms))
-        keys = ["force", "integrate", "pack", "unpack", "partition", "h2d", "d2h", "total"]
+        keys = ["force", "integrate", "pack", "unpack", "partition", "h2d", "d2h", "total", "pair", "bxb", "steps"]
         return dict(zip(keys, [float(x) for x in ms]))
 
     def counters(self) -> dict:

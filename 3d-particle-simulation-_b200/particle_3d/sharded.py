@@ -1,0 +1,91 @@
+"""One-process-per-GPU stepping over torch.distributed (NCCL on GPUs; gloo in the CPU tests).
+
+The path shards with ONE real exchange per step: every rank needs all positions
+to evaluate its share of the pair interactions.  Because the pair kernel evaluates each unordered
+block pair once and updates both particles, a rank's force pass yields partial forces for
+particles owned by other ranks, so the step is
+
+    shard_force      : this rank's block rows -> partial forces for all slots
+    all_reduce(sum)  : forces                               (16 B per slot)
+    shard_integrate  : this rank's slot range -> new positions of that range
+    all_gather       : new positions                        (16 B per slot)
+    shard_commit     : swap position buffers
+
+The engine is anything with the `Engine` shard API (particle_3d.Engine on GPUs; the tests
+substitute a CPU stand-in built on the oracle to cover the collective plumbing with gloo).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _abi
+
+
+class _CudaView:
+    """Exposes an engine-owned device buffer through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr: int, n_slots: int):
+        self.__cuda_array_interface__ = {
+            "shape": (n_slots, 4),
+            "typestr": "<f4",
+            "data": (ptr, False),
+            "version": 2,
+            "strides": None,
+        }
+
+
+def engine_tensors(engine, device_index: int):
+    """torch views (n_slots x 4 float32) of the engine's POS, POS_NEXT and FORCE buffers."""
+    import torch
+
+    out = {}
+    for name, which in (("pos", _abi.BUF_POS), ("pos_next", _abi.BUF_POS_NEXT), ("force", _abi.BUF_FORCE)):
+        ptr, n = engine.device_buffer(which)
+        out[name] = torch.as_tensor(_CudaView(ptr, n), device=f"cuda:{device_index}")
+    return out
+
+
+class ShardedStepper:
+    def __init__(self, engine, dist, rank: int, world: int, tensors_fn):
+        """tensors_fn() -> dict(pos=, pos_next=, force=) of torch tensors aliasing the engine's
+        CURRENT buffers (POS/POS_NEXT swap at every commit, so it is called once per parity)."""
+        self.engine, self.dist, self.rank, self.world = engine, dist, rank, world
+        self._tensors_fn = tensors_fn
+        self._views = [None, None]
+        self._parity = 0
+        self.collectives = 0
+
+    def _tensors(self):
+        if self._views[self._parity] is None:
+            self._views[self._parity] = self._tensors_fn()
+        return self._views[self._parity]
+
+    def step(self, params, ts: float, n_steps: int = 1):
+        eng, dist = self.engine, self.dist
+        for _ in range(n_steps):
+            t = self._tensors()
+            eng.shard_force(params)
+            if self.world > 1:
+                dist.all_reduce(t["force"], op=dist.ReduceOp.SUM)
+                self.collectives += 1
+            eng.shard_integrate(params, ts)
+            if self.world > 1:
+                s0, s1 = eng.shard_range()
+                # the send shard is copied first: not every backend accepts an input that aliases the output
+                dist.all_gather_into_tensor(t["pos_next"], t["pos_next"][s0:s1].clone())
+                self.collectives += 1
+            eng.shard_commit()
+            self._parity ^= 1
+
+
+def shard_slot_range(n_blocks: int, block: int, rank: int, world: int):
+    """Slot range [begin, end) rank `rank` integrates (same arithmetic as p3d_shard_range)."""
+    per = (n_blocks + world - 1) // world * block
+    n_slots = n_blocks * block
+    s0 = min(n_slots, rank * per)
+    return s0, min(n_slots, s0 + per)
+
+
+def shard_rows(n_blocks: int, rank: int, world: int) -> np.ndarray:
+    """Block rows whose pairs rank `rank` evaluates: rank, rank+world, ... (k_force_pair's row_stride)."""
+    return np.arange(rank, n_blocks, world)

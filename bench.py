@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py — the hot path of particle_3d (Particles::update, src/lib.rs:130-272) on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json config 4, the one its metric is quoted on): N = 1,048,576 particles,
+uniform cloud, W = 101.6 (density 1), default scene constants (src/bin/main.rs:133-148),
+ts = 1/60, seed 42.  A "step" is one update(): all-pairs force pass + fused integration.
+`value` = pair interactions per second (N^2 ordered pairs per step, the 20-flop convention's unit)
+with the state resident in HBM; `e2e` = the same through p3d_update with host buffers.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "3d-particle-simulation-_b200"))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_DEFAULT = 1_048_576
+W_DEFAULT = 101.6
+TS = float(np.float32(1.0 / 60.0))  # src/bin/main.rs:164,194
+SEED = 42
+FLOP_PER_INTERACTION = 20  # north_star's convention
+METRIC = "pair_interactions_per_s"
+UNIT = "interactions/s"
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.p = None
+
+    def __enter__(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+        return self
+
+    def __exit__(self, *a):
+        self.summary = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.p:
+            return
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            return
+        rows = [r.split(", ") for r in out.strip().splitlines() if r.count(",") >= 7]
+        if not rows:
+            return
+        clk = sorted(float(r[1]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in rows for k in range(4) if r[4 + k].strip().lower().startswith("active")})
+        self.summary = {"sm_mhz": clk[len(clk) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                        "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+def workload(n: int, W: float):
+    import particle_3d as p3
+
+    prm = p3.default_params_dict()
+    prm["world_size"] = W
+    return prm, p3.generate_particles(W, n, seed=SEED)
+
+
+def config_dict(n, W, extra=None):
+    c = {"workload": f"N={n} uniform cloud, W={W} (density 1), default scene constants (main.rs:133-148), ts=1/60, seed {SEED}; "
+                     "BASELINE.json configs[3]",
+         "n_particles": n, "world_size": W, "algorithm": "all-pairs (N^2 ordered pairs per step)",
+         "cache": "state is ~100 MB (< L2), so a 512 MiB buffer is overwritten between timed steps to flush L2"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_reference_sample(prm, parts, target_s: float, nthreads: int = 0):
+    """Times the CPU restatement of src/lib.rs (oracle, 'port') on a bounded sample of one step:
+    the counting sort over all N plus the per-particle pass for the first S particles."""
+    from oracle import oracle as O
+
+    n = len(parts)
+    probe = min(n, 4096)
+    _, st = O.update_sample(prm, TS, parts, 0, probe, mode=O.FAITHFUL, nthreads=nthreads)
+    per_particle = max(st["t_force_s"] / probe, 1e-9)
+    sample = int(min(n, max(probe, target_s / per_particle)))
+    _, st = O.update_sample(prm, TS, parts, 0, sample, mode=O.FAITHFUL, nthreads=nthreads)
+    step_s = st["t_build_s"] + st["t_force_s"] * (n / sample)
+    return {"step_s": step_s, "sample": sample, "build_s": st["t_build_s"], "force_sample_s": st["t_force_s"],
+            "cores": O.num_threads() if nthreads <= 0 else nthreads,
+            "candidates_per_particle": st["candidates"] / sample}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (spatial hash, 27x27 cell walk) on all
+    host threads.  The Rust crate cannot be built in this image (no cargo/rustc), so this is the C
+    restatement under oracle/ ('port').  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, W = args.n, args.world_size
+    prm, parts = workload(n, W)
+    per_step_budget = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    times, last = [], None
+    for s in range(args.warmup + args.steps):
+        last = cpu_reference_sample(prm, parts, per_step_budget)
+        if s >= args.warmup:
+            times.append(last["step_s"])
+    step_s = float(np.mean(times))
+    value = float(n) * n / step_s
+    sample_txt = (f"per step: counting sort over all {n} particles + per-particle pass for the first {last['sample']} "
+                  f"particles, scaled by N/sample (faithful mode, {last['cores']} OpenMP threads)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(n, W),
+        "steps_per_s": 1.0 / step_s,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": sample_txt,
+                         "ms_per_step": step_s * 1e3,
+                         "candidate_pairs_per_s": last["candidates_per_particle"] * n / step_s},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "all-pairs-equivalent N^2/t of the reference's cell-list algorithm; the Rust crate itself cannot be "
+                "built here (no cargo/rustc), this is the C restatement oracle/p3d_oracle.c",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def run_engine(args):
+    import torch
+
+    import particle_3d as p3
+    from particle_3d import _abi
+    from particle_3d.sharded import ShardedStepper, engine_tensors
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # noqa: F811
+
+        dist.init_process_group(backend="nccl", device_id=torch.device(f"cuda:{local}"))
+
+    n, W = args.n, args.world_size
+    prm, parts = workload(n, W)
+    P = p3.Engine.make_params(**prm)
+    eng = p3.Engine(local)
+    eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_PAIR if n >= 4096 else _abi.FORCE_REFERENCE_ORDER)
+    eng.set_option(_abi.OPT_BLOCK_SIZE, args.block)
+    eng.set_option(_abi.OPT_TIMING, 1)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_shard(rank, world)
+    eng.upload(parts, prm["id_count"])
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local}")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    stepper = None
+    if world > 1:
+        stepper = ShardedStepper(eng, dist, rank, world, lambda: engine_tensors(eng, local))
+
+    def one_step():
+        if stepper:
+            stepper.step(P, TS, 1)
+        else:
+            eng.step(P, TS, 1)
+
+    # ---------------- device-resident leg: `value` ----------------
+    for _ in range(args.warmup):
+        one_step()
+        flush.zero_()
+    barrier()
+    c0 = eng.counters()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern = {"force": 0.0, "pair": 0.0, "bxb": 0.0, "integrate": 0.0, "partition": 0.0, "steps": 0}
+    with ClockSampler(local) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            one_step()
+            if world == 1:
+                t = eng.timing()  # CUDA events recorded by the engine on this stream (syncs the stream)
+                for k in ("force", "pair", "bxb", "integrate", "partition"):
+                    kern[k] += t[k]
+                kern["steps"] += 1
+            flush.zero_()
+        ev1.record(stream)
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tt = torch.tensor([ms], device=f"cuda:{local}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    c1 = eng.counters()
+    ms_per_step = ms / args.steps
+    value = float(n) * n / (ms_per_step * 1e-3)
+    launches = (c1["kernels"] - c0["kernels"]) + args.steps  # + the L2-flush fill kernel per step
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": config_dict(n, W, {"parallelism": f"block rows sharded over {world} GPU(s); per step all-reduce(forces) + all-gather(positions) over NCCL" if world > 1 else "1 GPU",
+                                     "block": args.block}),
+        "steps_per_s": 1e3 / ms_per_step,
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary,
+    }
+
+    if world == 1 and rank == 0:
+        # ---------------- roofline of the dominant kernel (k_force_pair) ----------------
+        prop = torch.cuda.get_device_properties(local)
+        peaks = measured_peaks()
+        sm_max_mhz = (peaks or {}).get("sm_max_mhz") or clocks.summary.get("sm_max_mhz") or 1965.0
+        fp32_peak_tf = prop.multi_processor_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+        import ctypes as C
+        mb = (C.c_double * 4)()
+        _abi.load().p3d_microbench(local, 1, 2000, mb)  # packed FFMA2 microbenchmark
+        force_ms = kern["force"] / max(1, kern["steps"])
+        pair_ms = kern["pair"] / max(1, kern["steps"])
+        integ_ms = kern["integrate"] / max(1, kern["steps"])
+        flops = float(n) * n * FLOP_PER_INTERACTION
+        achieved_tf = flops / (force_ms * 1e-3) / 1e12
+        prof = {}
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "force_pair_ncu_summary.json")))
+        except Exception:
+            pass
+        line["roofline"] = {
+            "kernel": "force pass = k_force_pair (+ k_force_bxb for boundary x boundary blocks, + partition kernels)",
+            "bound": "fp32_fma", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s",
+            "frac": achieved_tf / fp32_peak_tf,
+            "peak_source": f"{prop.multi_processor_count} SMs x 128 lanes x 2 flop x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
+                           "tensor/HBM peaks do not bound this kernel (not a dense contraction)",
+            "peak_ffma2_microbench_tflops": mb[0] * 2 / 1e12,
+            "algorithmic_flops_per_launch": flops, "flop_per_interaction": FLOP_PER_INTERACTION,
+            "kernel_ms": force_ms, "pair_kernel_ms": pair_ms, "bxb_kernel_ms": kern["bxb"] / max(1, kern["steps"]),
+            "partition_ms": kern["partition"] / max(1, kern["steps"]),
+            "interactions_per_s_force_pass": float(n) * n / (force_ms * 1e-3),
+            "traffic": prof.get("dram_bytes_per_launch"),
+            "ncu": prof or None,
+        }
+        hbm = (peaks or {}).get("hbm_gbs") or 6650.0
+        ach = 80.0 * n / (integ_ms * 1e-3) / 1e9
+        line["roofline_integrate"] = {
+            "kernel": "k_integrate", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+            "algorithmic_bytes_per_particle": 80, "kernel_ms": integ_ms, "traffic": None,
+            "note": f"{80 * n / 1e6:.0f} MB working set; L2 is flushed between steps, but the force pass re-reads positions "
+                    "before integrate runs, so part of it is L2-resident",
+        }
+
+    # ---------------- end-to-end leg: p3d_update with pinned HOST buffers ----------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    if world == 1:
+        hin = torch.empty(n * 28, dtype=torch.uint8).pin_memory()
+        hout = torch.empty(n * 28, dtype=torch.uint8).pin_memory()
+        a_in = hin.numpy().view(_abi.PARTICLE)
+        a_out = hout.numpy().view(_abi.PARTICLE)
+        a_in[:] = parts
+        eng.set_option(_abi.OPT_TIMING, 0)
+        eng.update_into(P, TS, a_in, a_out)  # warm-up (allocations, first-touch)
+        a_in[:] = a_out
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.update_into(P, TS, a_in, a_out)  # synchronous: H2D + step + D2H
+            a_in, a_out = a_out, a_in            # src/lib.rs:167 swap
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        line["e2e"] = {"value": float(n) * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 28 + n * 4,
+                       "d2h_bytes_per_step": n * 28, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                       "api": "p3d_update(engine, params, ts, in, out, n) on pinned host arrays; wall clock around the synchronous call"}
+    else:
+        # multi-GPU e2e: every step uploads the full state from pinned host memory on every rank and
+        # reads the rank's shard back (the host mirror would do exactly this per update()).
+        hin = torch.empty(n * 28, dtype=torch.uint8).pin_memory()
+        a_in = hin.numpy().view(_abi.PARTICLE)
+        a_in[:] = parts
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.upload(a_in, prm["id_count"])
+            stepper._views = [None, None]
+            stepper._parity = 0
+            stepper.step(P, TS, 1)
+            out = eng.download()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        tt = torch.tensor([e2e_s], device=f"cuda:{local}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+        line["e2e"] = {"value": float(n) * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 28 + n * 4,
+                       "d2h_bytes_per_step": n * 28, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                       "api": "per rank: p3d_upload + sharded step + p3d_download on pinned host arrays"}
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
+    if world == 1 and rank == 0 and not args.no_cpu:
+        r = cpu_reference_sample(prm, parts, args.cpu_seconds)
+        line["cpu_baseline"] = {
+            "value": float(n) * n / r["step_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+            "sample": f"one step: counting sort over all {n} particles ({r['build_s']*1e3:.0f} ms) + per-particle pass for the first "
+                      f"{r['sample']} particles ({r['force_sample_s']:.2f} s), scaled by N/sample; C restatement of src/lib.rs "
+                      f"(spatial hash, faithful mode), {r['cores']} OpenMP threads",
+            "ms_per_step": r["step_s"] * 1e3, "steps_per_s": 1.0 / r["step_s"],
+            "candidate_pairs_per_s": r["candidates_per_particle"] * n / r["step_s"],
+        }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--world-size", type=float, default=None, help="box edge W (default: density 1)")
+    ap.add_argument("--block", type=int, default=256, choices=[128, 256])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.world_size is None:
+        args.world_size = W_DEFAULT if args.n == N_DEFAULT else round(float(args.n) ** (1.0 / 3.0), 1)
+    if args.warmup < 3:
+        args.warmup = 3  # timing rules: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -99,10 +99,12 @@ enum p3d_force_kernel {
 int p3d_set_option(p3d_engine *eng, int option, int value);
 int p3d_get_option(p3d_engine *eng, int option, int *value);
 
-/* Per-kernel device times of the most recent p3d_step/p3d_update (needs P3D_OPT_TIMING=1),
- * milliseconds summed over the steps of that call: [0]=force [1]=integrate [2]=pack(upload side)
- * [3]=unpack(download side) [4]=re-partition [5]=h2d copy [6]=d2h copy [7]=whole call. */
-int p3d_get_timing(p3d_engine *eng, float ms[8]);
+/* Per-kernel device times of the most recent p3d_step/p3d_update (needs P3D_OPT_TIMING=1), CUDA
+ * events on the engine stream, milliseconds summed over the timed steps of that call:
+ * [0]=whole force pass [1]=integrate kernel [2]=pack (upload side) [3]=unpack (download side)
+ * [4]=partition kernels + force memset [5]=h2d copy [6]=d2h copy [7]=force+integrate
+ * [8]=pair kernel alone [9]=boundary-x-boundary (+ out-of-box fallback) kernels [10]=timed steps [11]=0 */
+int p3d_get_timing(p3d_engine *eng, float ms[12]);
 /* Launch counters since creation: [0]=kernels launched, [1]=force kernels, [2]=integrate kernels. */
 int p3d_get_counters(p3d_engine *eng, uint64_t out[4]);
 
@@ -118,7 +120,8 @@ enum p3d_buffer {
 /* Device pointer + element count (slots, >= n because type segments are padded). */
 int p3d_device_buffer(p3d_engine *eng, int which, void **dev_ptr, size_t *n_slots);
 /* Shard = the slot range this rank integrates and, for the force pass, its share of block rows.
- * world==1 restores single-GPU behaviour. */
+ * world==1 restores single-GPU behaviour.  Call BEFORE p3d_upload: the slot layout is padded so that
+ * all ranks own equally many slots. */
 int p3d_set_shard(p3d_engine *eng, int rank, int world);
 int p3d_shard_range(p3d_engine *eng, size_t *slot_begin, size_t *slot_end);
 /* One step split at the collectives a multi-GPU driver inserts:

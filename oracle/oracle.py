@@ -45,10 +45,12 @@ class Stats(C.Structure):
         ("nonzero", C.c_uint64),
         ("dup_bucket_queries", C.c_uint64),
         ("affected", C.c_uint64),
+        ("t_build_s", C.c_double),
+        ("t_force_s", C.c_double),
     ]
 
     def asdict(self):
-        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+        return {k: (float(getattr(self, k)) if k.startswith("t_") else int(getattr(self, k))) for k, _ in self._fields_}
 
 
 def build(force: bool = False) -> str:
@@ -83,6 +85,9 @@ def lib():
             C.POINTER(_Params), C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
             C.c_void_p, C.c_void_p, C.POINTER(Stats), C.c_int,
         ]
+        L.ora_update_sample.restype = C.c_int
+        L.ora_update_sample.argtypes = [C.POINTER(_Params), C.c_float, C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.c_size_t, C.c_size_t, C.c_int, C.POINTER(Stats), C.c_int]
         L.ora_bruteforce_forces.restype = C.c_int
         L.ora_bruteforce_forces.argtypes = [C.POINTER(_Params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
         L.ora_integrate.restype = None
@@ -159,6 +164,22 @@ def update(params: dict, ts: float, particles: np.ndarray, mode: int = IDEAL, ac
     if rc:
         raise MemoryError("oracle allocation failed")
     return {"out": out, "force": force, "affected": aff, "stats": st.asdict()}
+
+
+def update_sample(params: dict, ts: float, particles: np.ndarray, i_begin: int, i_end: int, mode: int = FAITHFUL,
+                  nthreads: int = 0):
+    """Advance only particles [i_begin, i_end) of one step; returns (out, stats incl. t_build_s/t_force_s)."""
+    inp = np.ascontiguousarray(particles)
+    n = inp.shape[0]
+    i_end = min(i_end, n)
+    out = np.empty(max(i_end - i_begin, 0), dtype=PARTICLE)
+    st = Stats()
+    prm, _keep = _mk_params(params)
+    rc = lib().ora_update_sample(C.byref(prm), ts, inp.ctypes.data, out.ctypes.data, n, i_begin, i_end, mode,
+                                 C.byref(st), nthreads)
+    if rc:
+        raise AssertionError(f"oracle rc={rc}")
+    return out, st.asdict()
 
 
 def bruteforce_forces(params: dict, particles: np.ndarray, nthreads: int = 0) -> np.ndarray:

@@ -191,9 +191,38 @@ int ora_num_threads(void) {
 }
 
 /* lib.rs:130-272 */
+static int ora_update_impl(const ora_params *prm, float ts, const ora_particle *in, ora_particle *out,
+                           size_t n, size_t i_begin, size_t i_end, int mode, int acc64, float *force_out,
+                           uint8_t *affected, ora_stats *stats, int nthreads);
+
 int ora_update(const ora_params *prm, float ts, const ora_particle *in, ora_particle *out,
                size_t n, int mode, int acc64, float *force_out, uint8_t *affected,
                ora_stats *stats, int nthreads) {
+    return ora_update_impl(prm, ts, in, out, n, 0, n, mode, acc64, force_out, affected, stats, nthreads);
+}
+
+/* Same step, but only particles [i_begin, i_end) are advanced (out, force_out, affected hold
+ * i_end - i_begin entries).  The hash table is still built over all n particles.  Used by the
+ * bench to time a bounded sample of a large step. */
+int ora_update_sample(const ora_params *prm, float ts, const ora_particle *in, ora_particle *out,
+                      size_t n, size_t i_begin, size_t i_end, int mode, ora_stats *stats, int nthreads) {
+    if (i_end > n) i_end = n;
+    if (i_begin > i_end) i_begin = i_end;
+    return ora_update_impl(prm, ts, in, out, n, i_begin, i_end, mode, 0, NULL, NULL, stats, nthreads);
+}
+
+static double now_s(void) {
+#ifdef _OPENMP
+    return omp_get_wtime();
+#else
+    return 0.0;
+#endif
+}
+
+static int ora_update_impl(const ora_params *prm, float ts, const ora_particle *in, ora_particle *out,
+                           size_t n, size_t i_begin, size_t i_end, int mode, int acc64, float *force_out,
+                           uint8_t *affected, ora_stats *stats, int nthreads) {
+    const double t_start = now_s();
     const float W = prm->world_size, r = prm->particle_effect_radius, m = prm->min_pull_ratio;
     const uint32_t T = prm->id_count;
     if (stats) memset(stats, 0, sizeof(*stats));
@@ -228,13 +257,14 @@ int ora_update(const ora_params *prm, float ts, const ora_particle *in, ora_part
     }
     free(bucket_of);
     /* now table[b] = start of bucket b, table[b+1] = its end */
+    const double t_built = now_s();
 
     const float r2 = r * r; /* :218-219 */
     uint64_t s_cand = 0, s_in = 0, s_nz = 0, s_dupq = 0, s_aff = 0;
 
 #pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads) \
     reduction(+ : s_cand, s_in, s_nz, s_dupq, s_aff)
-    for (size_t i = 0; i < n; ++i) {
+    for (size_t i = i_begin; i < i_end; ++i) {
         const ora_particle p = in[i]; /* past_particles[i], :171-174 */
         float ax = 0.0f, ay = 0.0f, az = 0.0f;
         double dax = 0.0, day = 0.0, daz = 0.0;
@@ -297,16 +327,19 @@ int ora_update(const ora_params *prm, float ts, const ora_particle *in, ora_part
                 }
         if (acc64) { ax = (float)dax; ay = (float)day; az = (float)daz; }
         const float F[3] = {ax, ay, az};
-        if (force_out) { force_out[3 * i] = ax; force_out[3 * i + 1] = ay; force_out[3 * i + 2] = az; }
-        if (affected) affected[i] = (uint8_t)hit_dup;
+        const size_t o = i - i_begin;
+        if (force_out) { force_out[3 * o] = ax; force_out[3 * o + 1] = ay; force_out[3 * o + 2] = az; }
+        if (affected) affected[o] = (uint8_t)hit_dup;
         s_aff += (uint64_t)hit_dup;
         ora_particle u = p;
         integrate_one(prm, ts, F, &u); /* :245-264 */
-        out[i] = u;                     /* :266-268, index order preserved */
+        out[o] = u;                     /* :266-268, index order preserved */
     }
     if (stats) {
         stats->candidates = s_cand; stats->in_radius = s_in; stats->nonzero = s_nz;
         stats->dup_bucket_queries = s_dupq; stats->affected = s_aff;
+        stats->t_build_s = t_built - t_start;
+        stats->t_force_s = now_s() - t_built;
     }
     free(table);
     free(indices);

@@ -49,6 +49,8 @@ typedef struct {
     uint64_t nonzero;         /* in_radius with f != 0 */
     uint64_t dup_bucket_queries; /* (particle,image) queries whose 27 cells hit a bucket twice */
     uint64_t affected;        /* particles with a double-counted non-zero force */
+    double t_build_s;         /* wall time of the counting sort (lib.rs:135-164) */
+    double t_force_s;         /* wall time of the per-particle pass (lib.rs:171-268) */
 } ora_stats;
 
 /* Generic SipHash-c-d, 64-bit output (used with c=1,d=3,k=0/0 by hash_cell; c=2,d=4 for KATs). */
@@ -74,6 +76,11 @@ void ora_handle_wall_collision(float world_size, uint32_t walls, ora_particle *p
 int ora_update(const ora_params *prm, float ts, const ora_particle *in, ora_particle *out,
                size_t n, int mode, int acc64, float *force_out, uint8_t *affected,
                ora_stats *stats, int nthreads);
+
+/* Advance only particles [i_begin, i_end) (out holds i_end - i_begin entries); the hash table still
+ * covers all n.  For timing a bounded sample of a large step. */
+int ora_update_sample(const ora_params *prm, float ts, const ora_particle *in, ora_particle *out,
+                      size_t n, size_t i_begin, size_t i_end, int mode, ora_stats *stats, int nthreads);
 
 /* Independent check: O(N^2 * 27) brute force over all particles and all 27 image offsets in
  * double precision, same cutoff and force law, each (j,image) counted once.  force_out n*3 doubles. */

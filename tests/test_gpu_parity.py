@@ -1,0 +1,305 @@
+"""GPU parity: the CUDA path (through the C ABI, libp3d.so) against the CPU oracle.
+
+Tolerance (north_star): per-particle relative 1e-5 after one step, with the floors of
+SURVEY.md §8d (see helpers.parity_errors).  Index order and ids must be preserved bit-exactly.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import particle_3d as p3
+from particle_3d import _abi
+from oracle import oracle as O
+
+from helpers import assert_parity, parity_errors, pos, vel
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TS = float(np.float32(1.0 / 60.0))
+KERNELS = [_abi.FORCE_REFERENCE_ORDER, _abi.FORCE_PAIR]
+IDS = ["reference_order", "pair"]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = p3.Engine(0)
+    yield e
+    e.close()
+
+
+def gpu_update(eng, prm, parts, kernel, ts=TS, block=128):
+    eng.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+    eng.set_option(_abi.OPT_BLOCK_SIZE, block)
+    return eng.update(p3.Engine.make_params(**prm), ts, parts)
+
+
+# ---------------------------------------------------------------- golden fixtures / configs
+@pytest.mark.parametrize("kernel", KERNELS, ids=IDS)
+def test_config1_default_scene_one_step_vs_golden(eng, default_params, kernel):
+    g = np.load(os.path.join(GOLD, "default_scene_n1000_seed42.npz"))
+    out = gpu_update(eng, default_params, g["start"], kernel)
+    assert_parity(out, g["ideal_step1"], 10.0, what="config 1 vs ideal oracle")
+    # faithful (reference quirk, Appendix B.1): identical except for the particles the oracle flags
+    assert_parity(out, g["faithful_step1"], 10.0, mask=g["affected1"] == 0, what="config 1 vs faithful oracle")
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=IDS)
+def test_config1_forces_vs_golden(eng, default_params, kernel):
+    g = np.load(os.path.join(GOLD, "default_scene_n1000_seed42.npz"))
+    gpu_update(eng, default_params, g["start"], kernel)
+    f = eng.download_forces().astype(np.float64)
+    fr = g["ideal_force1"].astype(np.float64)
+    frms = np.sqrt((fr ** 2).sum(1).mean())
+    err = np.linalg.norm(f - fr, axis=1) / np.maximum(np.linalg.norm(fr, axis=1), frms)
+    assert err.max() < 1e-5
+
+
+def test_config1_100_steps_reference_order(eng, default_params):
+    """100 steps, stepping through the drop-in call every step (as main.rs:199 does)."""
+    g = np.load(os.path.join(GOLD, "default_scene_n1000_seed42.npz"))
+    cur = g["start"].copy()
+    for _ in range(100):
+        cur = gpu_update(eng, default_params, cur, _abi.FORCE_REFERENCE_ORDER)
+    ref = g["ideal_step100"]
+    # f32 summation-order noise grows chaotically (max|dp| ~3e-5 at 100 steps
+    # between f32 and f64 runs); compare aggregates tightly and particles loosely.
+    ke, ker = 0.5 * (vel(cur) ** 2).sum(), g["ideal_ke"][-1]
+    assert abs(ke - ker) / ker < 1e-4
+    dpos = np.linalg.norm(pos(cur) - pos(ref), axis=1)
+    dpos = np.minimum(dpos, 10.0 - dpos)  # a particle may sit on the other side of the wrap
+    assert np.median(dpos) < 1e-5 and dpos.max() < 5e-3
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=IDS)
+def test_uniform_4096_golden(eng, default_params, kernel):
+    g = np.load(os.path.join(GOLD, "uniform_n4096_seed7.npz"))
+    prm = dict(default_params, world_size=16.0)
+    assert_parity(gpu_update(eng, prm, g["start"], kernel), g["ideal_step1"], 16.0)
+    prm = dict(prm, walls=True, acceleration=(0.0, -9.8, 0.0))
+    assert_parity(gpu_update(eng, prm, g["start"], kernel), g["ideal_walls_gravity_step1"], 16.0)
+
+
+@pytest.mark.parametrize("block", [128, 256])
+def test_config2_16k_uniform(eng, default_params, block):
+    W = 25.4
+    prm = dict(default_params, world_size=W)
+    start = p3.generate_particles(W, 16384, seed=42)
+    ref = O.update(prm, TS, start, mode=O.IDEAL)["out"]
+    out = gpu_update(eng, prm, start, _abi.FORCE_PAIR, block=block)
+    assert_parity(out, ref, W, what=f"config 2 block={block}")
+    out2 = gpu_update(eng, prm, start, _abi.FORCE_REFERENCE_ORDER)
+    assert_parity(out2, ref, W, what="config 2 reference-order kernel")
+
+
+def test_plummer_cluster_one_step(eng, default_params):
+    W = 64.0
+    prm = dict(default_params, world_size=W)
+    start = p3.generate_plummer(W, 30000, W / 6, seed=42)
+    ref = O.update(prm, TS, start, mode=O.IDEAL)["out"]
+    assert_parity(gpu_update(eng, prm, start, _abi.FORCE_PAIR), ref, W, what="plummer")
+
+
+# ---------------------------------------------------------------- hand-derived known answers
+@pytest.mark.parametrize("kernel", KERNELS, ids=IDS)
+def test_two_body_kat(eng, default_params, kernel):
+    p = np.zeros(2, _abi.PARTICLE)
+    p[1]["px"], p[1]["id"] = 0.65, 1
+    out = gpu_update(eng, default_params, p, kernel)
+    v = (2.0 / 60.0) * (1 - 0.97 / 60.0)
+    assert out[0]["vx"] == pytest.approx(v, rel=2e-6) and out[1]["vx"] == pytest.approx(-v, rel=2e-6)
+    assert out[0]["px"] == pytest.approx(v / 60, rel=2e-6)
+    p[1]["id"] = 4  # asymmetric matrix: both accelerate toward -x
+    out = gpu_update(eng, default_params, p, kernel)
+    assert out[0]["vx"] == pytest.approx(-v, rel=2e-6) and out[1]["vx"] == pytest.approx(-v, rel=2e-6)
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=IDS)
+@pytest.mark.parametrize("walls", [False, True])
+def test_periodic_image_kat(eng, default_params, kernel, walls):
+    p = np.zeros(2, _abi.PARTICLE)
+    p[0]["px"], p[1]["px"] = 4.9, -4.9
+    prm = dict(default_params, walls=walls)
+    gpu_update(eng, prm, p, kernel)
+    f = eng.download_forces()
+    assert f[0, 0] == pytest.approx(-1 / 3, rel=1e-5) and f[1, 0] == pytest.approx(1 / 3, rel=1e-5)
+
+
+# ---------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("kernel", KERNELS, ids=IDS)
+def test_empty_single_and_coincident(eng, default_params, kernel):
+    assert gpu_update(eng, default_params, np.zeros(0, _abi.PARTICLE), kernel).shape == (0,)
+    p = np.zeros(1, _abi.PARTICLE)
+    p[0]["px"], p[0]["vy"] = 1.0, 0.5
+    ref = O.update(default_params, TS, p)["out"]
+    assert gpu_update(eng, default_params, p, kernel).tobytes() == ref.tobytes()
+    p = np.zeros(3, _abi.PARTICLE)
+    p["px"] = 1.25  # coincident: d2 == 0 is skipped (src/lib.rs:216)
+    out = gpu_update(eng, default_params, p, kernel)
+    assert not vel(out).any()
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=IDS)
+@pytest.mark.parametrize(
+    "over",
+    [
+        dict(min_pull_ratio=0.0),
+        dict(min_pull_ratio=1.0),
+        dict(min_pull_ratio=0.9),
+        dict(particle_effect_radius=0.7),          # r < 1: the cutoff bites inside the force range
+        dict(particle_effect_radius=0.25, min_pull_ratio=0.5),
+        dict(interaction_force=10.0, coefficient=0.0),
+        dict(coefficient=1.0),
+        dict(walls=True, acceleration=(0.3, -9.8, 1.0)),
+        dict(world_size=4.0),                       # W == 2r: every particle is a boundary particle
+    ],
+    ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()),
+)
+def test_parameter_edges(eng, default_params, kernel, over):
+    prm = dict(default_params, **over)
+    W = prm["world_size"]
+    start = p3.generate_particles(W, 3000, seed=11)
+    start["vx"] = np.linspace(-1, 1, 3000, dtype=np.float32)
+    ref = O.update(prm, TS, start, mode=O.IDEAL)["out"]
+    assert_parity(gpu_update(eng, prm, start, kernel), ref, W, what=str(over))
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=IDS)
+def test_drag_clamp_large_timestep(eng, default_params, kernel):
+    start = p3.generate_particles(10.0, 500, seed=3)
+    start["vy"] = 2.0
+    prm = dict(default_params, coefficient=1.0)
+    ref = O.update(prm, 2.0, start, mode=O.IDEAL)["out"]
+    out = gpu_update(eng, prm, start, kernel, ts=2.0)
+    assert_parity(out, ref, 10.0)
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=IDS)
+def test_positions_outside_the_box(eng, default_params, kernel):
+    """Callers may hand over any positions; images -1,0,+1 are still searched (src/lib.rs:177-185)."""
+    start = p3.generate_particles(10.0, 2000, seed=5)
+    start["px"][::7] += 10.0   # one box to the right
+    start["py"][::11] -= 10.0
+    start["pz"][::13] += 23.0  # beyond every image
+    ref = O.update(default_params, TS, start, mode=O.IDEAL)["out"]
+    assert_parity(gpu_update(eng, default_params, start, kernel), ref, 10.0)
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=IDS)
+def test_fast_particle_single_wrap(eng, default_params, kernel):
+    start = p3.generate_particles(10.0, 600, seed=8)
+    start["vx"][0] = 900.0  # moves 15 units in one step: wrapped once only (src/lib.rs:74-92)
+    prm = dict(default_params, coefficient=0.0)
+    ref = O.update(prm, TS, start, mode=O.IDEAL)["out"]
+    out = gpu_update(eng, prm, start, kernel)
+    assert_parity(out, ref, 10.0)
+    assert out[0]["px"] == ref[0]["px"] and abs(out[0]["px"]) > 5.0
+
+
+def test_device_resident_steps_handle_out_of_box_state(eng, default_params):
+    """p3d_step keeps state on the device; a particle leaving the box must flip the next step to
+    the all-image kernel without host intervention."""
+    start = p3.generate_particles(10.0, 5000, seed=9)
+    start["vx"][:5] = 900.0
+    prm = dict(default_params, coefficient=0.0)
+    P = p3.Engine.make_params(**prm)
+    eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_PAIR)
+    eng.upload(start, 5)
+    eng.step(P, TS, 3)
+    out = eng.download()
+    ref = start
+    for _ in range(3):
+        ref = O.update(prm, TS, ref, mode=O.IDEAL)["out"]
+    dv, dp = parity_errors(out, ref, 10.0)
+    assert dv.max() < 5e-5 and dp.max() < 5e-5  # three steps of accumulated rounding
+
+
+def test_many_types_and_single_type(eng, default_params):
+    rng = np.random.default_rng(0)
+    for T in (1, 64):
+        A = rng.uniform(-1, 1, T * T).astype(np.float32)
+        prm = dict(default_params, id_count=T, attraction_matrix=list(A), world_size=12.0)
+        start = p3.generate_particles(12.0, 6000, seed=2, id_count=T)
+        ref = O.update(prm, TS, start, mode=O.IDEAL)["out"]
+        for kernel in KERNELS:
+            assert_parity(gpu_update(eng, prm, start, kernel), ref, 12.0, what=f"T={T}")
+
+
+# ---------------------------------------------------------------- API semantics / errors
+def test_errors_match_reference_panics(eng, default_params):
+    p = np.zeros(4, _abi.PARTICLE)
+    with pytest.raises(AssertionError):  # src/lib.rs:132
+        gpu_update(eng, dict(default_params, world_size=3.99), p, _abi.FORCE_AUTO)
+    p[2]["id"] = 5
+    with pytest.raises(IndexError):      # src/lib.rs:225-228
+        gpu_update(eng, default_params, p, _abi.FORCE_AUTO)
+    with pytest.raises(p3.P3DError):
+        gpu_update(eng, dict(default_params, id_count=65, attraction_matrix=[0.0] * 65 * 65), np.zeros(1, _abi.PARTICLE),
+                   _abi.FORCE_AUTO)
+
+
+def test_particles_update_semantics(default_params):
+    """past_particles = pre-step state, active = post-step, return value is a copy; N and every
+    parameter may change between calls (src/lib.rs:167-171,268-271; main.rs:263-359)."""
+    sim = p3.default_scene(n=1000, seed=42)
+    before = sim.active_particles.copy()
+    ret = sim.update(TS)
+    assert sim.past_particles.tobytes() == before.tobytes()
+    assert ret.tobytes() == sim.active_particles.tobytes() and ret is not sim.active_particles
+    ref = O.update(default_params, TS, before, mode=O.IDEAL)["out"]
+    assert_parity(ret, ref, 10.0)
+    # the UI truncates / extends the Vec and edits parameters between steps
+    sim.active_particles = np.concatenate([sim.active_particles[:700], p3.generate_particles(10.0, 900, seed=1)])
+    sim.walls, sim.min_pull_ratio, sim.acceleration = True, 0.45, (0.0, -1.0, 0.0)
+    sim.attraction_matrix[7] = -0.25
+    before = sim.active_particles.copy()
+    prm = dict(default_params, walls=True, min_pull_ratio=0.45, acceleration=(0.0, -1.0, 0.0),
+               attraction_matrix=list(sim.attraction_matrix))
+    ret = sim.update(TS)
+    assert len(ret) == 1600
+    assert_parity(ret, O.update(prm, TS, before, mode=O.IDEAL)["out"], 10.0)
+
+
+def test_auto_kernel_selection_and_counters(eng, default_params):
+    eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_AUTO)
+    c0 = eng.counters()
+    eng.update(p3.Engine.make_params(**default_params), TS, p3.generate_particles(10.0, 1000, seed=1))
+    c1 = eng.counters()
+    assert c1["force"] - c0["force"] == 1 and c1["integrate"] - c0["integrate"] == 1
+    prm = dict(default_params, world_size=20.0)
+    eng.update(p3.Engine.make_params(**prm), TS, p3.generate_particles(20.0, 8000, seed=1))
+    c2 = eng.counters()
+    assert c2["force"] - c1["force"] == 2  # pair kernel + boundary x boundary kernel
+
+
+# ---------------------------------------------------------------- size-independent properties at scale
+def test_pair_kernel_agrees_with_reference_order_kernel_at_262k(eng, default_params):
+    """At N = 262,144 the CPU oracle is slow; the exact reference-order CUDA kernel (itself
+    oracle-checked above) is the comparison."""
+    W = 64.0
+    prm = dict(default_params, world_size=W)
+    start = p3.generate_plummer(W, 262144, W / 6, seed=42)
+    a = gpu_update(eng, prm, start, _abi.FORCE_PAIR)
+    b = gpu_update(eng, prm, start, _abi.FORCE_REFERENCE_ORDER)
+    assert_parity(a, b, W, what="pair vs reference-order at 262k")
+
+
+def test_newton_third_law_with_symmetric_matrix_at_1m(eng, default_params):
+    """With a symmetric attraction matrix every pair force is equal and opposite, so the total
+    force vanishes — a checksum over all 1.1e12 interactions at BASELINE.json's full size."""
+    W = 101.6
+    A = np.array(default_params["attraction_matrix"], np.float32).reshape(5, 5)
+    A = ((A + A.T) / 2).ravel()
+    prm = dict(default_params, world_size=W, attraction_matrix=list(A))
+    start = p3.generate_particles(W, 1048576, seed=42)
+    eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_PAIR)
+    eng.upload(start, 5)
+    eng.step(p3.Engine.make_params(**prm), TS, 1)
+    f = eng.download_forces().astype(np.float64)
+    assert np.isfinite(f).all()
+    assert np.abs(f.sum(0)).max() / np.abs(f).sum() < 1e-6
+    # a sample of particles against the oracle's brute-force-free cell walk
+    ref = O.update(prm, TS, start, mode=O.IDEAL, want_force=True)["force"].astype(np.float64)
+    frms = np.sqrt((ref ** 2).sum(1).mean())
+    err = np.linalg.norm(f - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), frms)
+    assert err.max() < 1e-5
