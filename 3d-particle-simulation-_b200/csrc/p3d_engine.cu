@@ -88,6 +88,7 @@ struct p3d_engine {
     DevBuf<uint32_t> perm, slot_of, sidx;
     DevBuf<uint8_t> seg_type, bclass;
     DevBuf<int> seg_start, seg_end, cnt;
+    DevBuf<int2> cta_cnt, cta_off;
     DevBuf<float> aos, fout, sx, sy, sz;
     DevBuf<float> matrix;
     DevBuf<int> flags;      // [0],[1]: out-of-box flags (double-buffered by step parity)
@@ -223,6 +224,8 @@ int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T) {
     if ((rc = e->seg_start.ensure(P3D_MAX_TYPES))) return rc;
     if ((rc = e->seg_end.ensure(P3D_MAX_TYPES))) return rc;
     if ((rc = e->cnt.ensure(2 * P3D_MAX_TYPES))) return rc;
+    if ((rc = e->cta_cnt.ensure(ns / kPartThreads + 1))) return rc;
+    if ((rc = e->cta_off.ensure(ns / kPartThreads + 1))) return rc;
     if ((rc = e->aos.ensure((n ? n : 1) * 7))) return rc;
     if ((rc = e->matrix.ensure(P3D_MAX_TYPES * P3D_MAX_TYPES))) return rc;
     if ((rc = e->flags.ensure(4))) return rc;
@@ -302,13 +305,16 @@ int launch_force(p3d_engine *e, const DevParams &P) {
     const int B = e->B;
     const float margin = std::max(1.0e-3f, 1.0e-5f * P.W);
     const float interior_limit = e->opt_block_sort ? (P.half - P.reach - margin) : -1.0f;
-    CU(cudaMemsetAsync(e->cnt.p, 0, 2 * P3D_MAX_TYPES * sizeof(int), st));
-    k_part<<<(ns + 255) / 256, 256, 0, st>>>(pos, ns, B, e->seg_type.p, e->seg_start.p, e->seg_end.p, e->cnt.p,
-                                            e->spos.p, e->sx.p, e->sy.p, e->sz.p, e->sidx.p, interior_limit, flag_next);
+    const int part_ctas = ns / kPartThreads;  // n_slots is a multiple of B >= 128
+    k_part_count<<<part_ctas, kPartThreads, 0, st>>>(pos, ns, interior_limit, e->cta_cnt.p, flag_next);
+    k_part_scan<<<P.T, 1024, 0, st>>>(e->cta_cnt.p, e->cta_off.p, e->seg_start.p, e->seg_end.p, e->cnt.p);
+    k_part_scatter<<<part_ctas, kPartThreads, 0, st>>>(pos, ns, B, e->seg_type.p, e->seg_start.p, e->seg_end.p,
+                                                       e->cta_off.p, e->spos.p, e->sx.p, e->sy.p, e->sz.p,
+                                                       e->sidx.p, interior_limit);
     k_part_fill<<<(ns + 255) / 256, 256, 0, st>>>(ns, B, e->seg_type.p, e->seg_start.p, e->seg_end.p, e->cnt.p,
                                                  e->spos.p, e->sx.p, e->sy.p, e->sz.p, e->sidx.p, e->bclass.p);
     CU(cudaMemsetAsync(e->frc.p, 0, (size_t)ns * sizeof(float4), st));
-    e->counters[0] += 2;
+    e->counters[0] += 4;
     if (e->step_ev) CU(cudaEventRecord(e->step_ev[1], st));
 
     const int M = e->M;
@@ -466,7 +472,7 @@ void p3d_destroy(p3d_engine *e) {
     e->vel.release(); e->frc.release(); e->spos.release();
     e->perm.release(); e->slot_of.release(); e->sidx.release();
     e->seg_type.release(); e->bclass.release();
-    e->seg_start.release(); e->seg_end.release(); e->cnt.release();
+    e->seg_start.release(); e->seg_end.release(); e->cnt.release(); e->cta_cnt.release(); e->cta_off.release();
     e->aos.release(); e->fout.release(); e->sx.release(); e->sy.release(); e->sz.release(); e->matrix.release(); e->flags.release(); e->diag.release();
     if (e->pin) cudaFreeHost(e->pin);
     for (auto x : e->ev) cudaEventDestroy(x);

@@ -22,44 +22,113 @@
 enum : uint8_t { P3D_BLK_INTERIOR = 0, P3D_BLK_BOUNDARY = 1, P3D_BLK_EMPTY = 2 };
 
 // ---------------------------------------------------------------------------------------------
-// Partition pass, part 1: stage every live slot into its type's region of the block list —
-// interior particles packed upward from the region start, boundary particles downward from its
-// end.  One warp covers 32 consecutive slots, which always share a type (segments are padded to
-// multiples of B >= 32), so a single atomic per class per warp reserves the destinations.
-__global__ void __launch_bounds__(256) k_part(const float4 *__restrict__ pos, int n_slots, int B,
-                                              const uint8_t *__restrict__ seg_type,
-                                              const int *__restrict__ seg_start, const int *__restrict__ seg_end,
-                                              int *__restrict__ cnt, float4 *__restrict__ spos,
-                                              float *__restrict__ sx, float *__restrict__ sy,
-                                              float *__restrict__ sz, uint32_t *__restrict__ sidx,
-                                              float interior_limit, int *__restrict__ flag_to_clear) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// Partition pass.  Every step each type's live slots are staged as [interior ... ghosts ... boundary]
+// in slot order (a STABLE partition: count -> scan -> scatter, no atomics), so that every rank of a
+// multi-GPU run derives bit-identical block lists from the same positions.
+// CTAs of 128 threads never straddle two types (type segments are multiples of B >= 128).
+constexpr int kPartThreads = 128;
+
+__device__ __forceinline__ bool part_is_interior(const float4 p, float interior_limit) {
+    return fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z))) < interior_limit;
+}
+
+// part 1a: per-CTA counts of interior / boundary particles.
+__global__ void __launch_bounds__(kPartThreads) k_part_count(const float4 *__restrict__ pos, int n_slots,
+                                                             float interior_limit, int2 *__restrict__ cta_cnt,
+                                                             int *__restrict__ flag_to_clear) {
+    const int s = blockIdx.x * kPartThreads + threadIdx.x;
     if (s == 0) *flag_to_clear = 0;
-    if (s >= n_slots) return;  // n_slots is a multiple of 32: whole warps leave together
-    const float4 p = pos[s];
-    const bool live = f2u(p.w) != P3D_GHOST_ID;
-    const int t = seg_type[s / B];
-    const float amax = fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z)));
-    const bool interior = live && (amax < interior_limit);
-    const bool boundary = live && !interior;
+    bool interior = false, boundary = false;
+    if (s < n_slots) {
+        const float4 p = pos[s];
+        const bool live = f2u(p.w) != P3D_GHOST_ID;
+        interior = live && part_is_interior(p, interior_limit);
+        boundary = live && !interior;
+    }
+    const int ni = __syncthreads_count(interior);
+    const int nb = __syncthreads_count(boundary);
+    if (threadIdx.x == 0) cta_cnt[blockIdx.x] = make_int2(ni, nb);
+}
+
+// part 1b: one CTA per type scans the per-CTA counts of that type's segment (exclusive prefix),
+// and records the type totals in cnt[2t], cnt[2t+1].
+__global__ void __launch_bounds__(1024) k_part_scan(const int2 *__restrict__ cta_cnt, int2 *__restrict__ cta_off,
+                                                    const int *__restrict__ seg_start,
+                                                    const int *__restrict__ seg_end, int *__restrict__ cnt) {
+    const int t = blockIdx.x;
+    const int c0 = seg_start[t] / kPartThreads, c1 = seg_end[t] / kPartThreads;
+    __shared__ int2 warp_tot[32];
+    __shared__ int2 carry;
+    if (threadIdx.x == 0) carry = make_int2(0, 0);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = c0; base < c1; base += 1024) {
+        const int c = base + threadIdx.x;
+        int2 v = (c < c1) ? cta_cnt[c] : make_int2(0, 0);
+        int2 inc = v;  // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ax = __shfl_up_sync(0xffffffffu, inc.x, o), ay = __shfl_up_sync(0xffffffffu, inc.y, o);
+            if (lane >= o) { inc.x += ax; inc.y += ay; }
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int2 w = warp_tot[lane];
+            int2 winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ax = __shfl_up_sync(0xffffffffu, winc.x, o), ay = __shfl_up_sync(0xffffffffu, winc.y, o);
+                if (lane >= o) { winc.x += ax; winc.y += ay; }
+            }
+            warp_tot[lane] = make_int2(winc.x - w.x, winc.y - w.y);  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int2 wbase = warp_tot[warp];
+        const int2 cbase = carry;
+        if (c < c1) cta_off[c] = make_int2(cbase.x + wbase.x + inc.x - v.x, cbase.y + wbase.y + inc.y - v.y);
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = make_int2(cbase.x + wbase.x + inc.x, cbase.y + wbase.y + inc.y);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        cnt[2 * t] = carry.x;
+        cnt[2 * t + 1] = carry.y;
+    }
+}
+
+// part 1c: scatter.  Interior particles are packed upward from the region start, boundary particles
+// downward from its end, both in slot order.
+__global__ void __launch_bounds__(kPartThreads) k_part_scatter(
+    const float4 *__restrict__ pos, int n_slots, int B, const uint8_t *__restrict__ seg_type,
+    const int *__restrict__ seg_start, const int *__restrict__ seg_end, const int2 *__restrict__ cta_off,
+    float4 *__restrict__ spos, float *__restrict__ sx, float *__restrict__ sy, float *__restrict__ sz,
+    uint32_t *__restrict__ sidx, float interior_limit) {
+    const int s = blockIdx.x * kPartThreads + threadIdx.x;
+    bool interior = false, boundary = false;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s < n_slots) {
+        p = pos[s];
+        const bool live = f2u(p.w) != P3D_GHOST_ID;
+        interior = live && part_is_interior(p, interior_limit);
+        boundary = live && !interior;
+    }
     const unsigned mi = __ballot_sync(0xffffffffu, interior);
     const unsigned mb = __ballot_sync(0xffffffffu, boundary);
-    const int lane = threadIdx.x & 31;
-    int bi = 0, bb = 0;
-    if (lane == 0) {
-        if (mi) bi = atomicAdd(cnt + 2 * t, __popc(mi));
-        if (mb) bb = atomicAdd(cnt + 2 * t + 1, __popc(mb));
-    }
-    bi = __shfl_sync(0xffffffffu, bi, 0);
-    bb = __shfl_sync(0xffffffffu, bb, 0);
+    __shared__ int2 wcnt[kPartThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) wcnt[warp] = make_int2(__popc(mi), __popc(mb));
+    __syncthreads();
+    int wi = 0, wb = 0;
+    for (int w = 0; w < warp; ++w) { wi += wcnt[w].x; wb += wcnt[w].y; }
+    if (s >= n_slots) return;
+    const int t = seg_type[(blockIdx.x * kPartThreads) / B];
+    const int2 off = cta_off[blockIdx.x];
     const unsigned lt = (1u << lane) - 1u;
-    if (interior) {
-        const int dst = seg_start[t] + bi + __popc(mi & lt);
-        spos[dst] = p;
-        sx[dst] = p.x; sy[dst] = p.y; sz[dst] = p.z;
-        sidx[dst] = (uint32_t)s;
-    } else if (boundary) {
-        const int dst = seg_end[t] - 1 - (bb + __popc(mb & lt));
+    int dst = -1;
+    if (interior) dst = seg_start[t] + off.x + wi + __popc(mi & lt);
+    else if (boundary) dst = seg_end[t] - 1 - (off.y + wb + __popc(mb & lt));
+    if (dst >= 0) {
         spos[dst] = p;
         sx[dst] = p.x; sy[dst] = p.y; sz[dst] = p.z;
         sidx[dst] = (uint32_t)s;

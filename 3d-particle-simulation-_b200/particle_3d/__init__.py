@@ -133,8 +133,14 @@ class Engine:
         _abi.check(self._lib.p3d_get_counters(self._h, c))
         return {"kernels": int(c[0]), "force": int(c[1]), "integrate": int(c[2])}
 
-    def set_stream(self, cuda_stream_ptr: int):
-        _abi.check(self._lib.p3d_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+    def set_stream(self, cuda_stream_ptr):
+        """Run on the given cudaStream_t.  torch reports its default stream as handle 0, which the ABI
+        reads as "engine's own stream"; 0 is therefore passed as cudaStreamLegacy (0x1).  None = own stream."""
+        if cuda_stream_ptr is None:
+            ptr = 0
+        else:
+            ptr = int(cuda_stream_ptr) or 1
+        _abi.check(self._lib.p3d_set_stream(self._h, C.c_void_p(ptr)))
 
     def device_buffer(self, which: int):
         p, n = C.c_void_p(), C.c_size_t()

@@ -180,7 +180,8 @@ def run_engine(args):
     eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_PAIR if n >= 4096 else _abi.FORCE_REFERENCE_ORDER)
     eng.set_option(_abi.OPT_BLOCK_SIZE, args.block)
     eng.set_option(_abi.OPT_TIMING, 1)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=local)  # every launch, copy and collective of the bench runs on this stream
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     eng.set_shard(rank, world)
     eng.upload(parts, prm["id_count"])

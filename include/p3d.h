@@ -109,7 +109,8 @@ int p3d_get_timing(p3d_engine *eng, float ms[12]);
 int p3d_get_counters(p3d_engine *eng, uint64_t out[4]);
 
 /* ---- plumbing for one-process-per-GPU drivers (torch.distributed owns the collective) ---- */
-/* Run every subsequent launch on this cudaStream_t (e.g. torch's current stream); NULL = own stream. */
+/* Run every subsequent launch on this cudaStream_t (e.g. torch's current stream); NULL = own stream
+ * (pass cudaStreamLegacy, (cudaStream_t)0x1, to name the legacy default stream). */
 int p3d_set_stream(p3d_engine *eng, void *cuda_stream);
 enum p3d_buffer {
     P3D_BUF_POS = 0,      /* float4 {x,y,z,id bits} per slot, current positions */

@@ -303,3 +303,36 @@ def test_newton_third_law_with_symmetric_matrix_at_1m(eng, default_params):
     frms = np.sqrt((ref ** 2).sum(1).mean())
     err = np.linalg.norm(f - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), frms)
     assert err.max() < 1e-5
+
+
+# ---------------------------------------------------------------- sharding, emulated on one GPU
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("kernel", KERNELS, ids=IDS)
+def test_shard_partial_forces_sum_to_the_full_force(default_params, kernel, world):
+    """Each rank evaluates its share of the block rows; the driver sums the partial forces.
+    Emulated by running every rank's force pass in turn on one device (B200_PROFILING.md: never
+    run ranks that wait on each other on one GPU — these do not wait)."""
+    W, n = 30.0, 27000
+    prm = dict(default_params, world_size=W)
+    parts = p3.generate_particles(W, n, seed=42)
+    ref = O.update(prm, TS, parts, mode=O.IDEAL, want_force=True)["force"].astype(np.float64)
+    P = p3.Engine.make_params(**prm)
+    e = p3.Engine(0)
+    e.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+    e.set_shard(0, world)
+    e.upload(parts, 5)
+    total = np.zeros((n, 3))
+    ranges = []
+    for r in range(world):
+        e.set_shard(r, world)
+        e.shard_force(P)
+        e.sync()
+        total += e.download_forces()
+        ranges.append(e.shard_range())
+    e.close()
+    frms = np.sqrt((ref ** 2).sum(1).mean())
+    err = np.linalg.norm(total - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), frms)
+    assert err.max() < 1e-5
+    # the integrate ranges tile the slot array without gaps or overlap
+    assert ranges[0][0] == 0 and all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+    assert len({b - a for a, b in ranges}) == 1

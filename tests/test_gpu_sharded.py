@@ -1,0 +1,70 @@
+"""Multi-GPU sharded stepping on real GPUs (skipped when fewer than 2 are visible)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.path.join(ROOT, "3d-particle-simulation-_b200")); sys.path.insert(0, ROOT)
+import particle_3d as p3
+from particle_3d import _abi
+from particle_3d.sharded import ShardedStepper, engine_tensors
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+W, n, steps = 30.0, 27000, 3
+prm = dict(p3.default_params_dict(), world_size=W)
+parts = p3.generate_particles(W, n, seed=42)
+P = p3.Engine.make_params(**prm)
+eng = p3.Engine(local)
+eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_PAIR)
+s = torch.cuda.Stream(device=local); torch.cuda.set_stream(s); eng.set_stream(s.cuda_stream)
+eng.set_shard(rank, world)
+eng.upload(parts, 5)
+st = ShardedStepper(eng, dist, rank, world, lambda: engine_tensors(eng, local))
+st.step(P, 1/60, steps)
+torch.cuda.synchronize()
+out = eng.download()
+s0, s1 = eng.shard_range()
+np.save(os.path.join(OUT, f"shard_{rank}.npy"), out)
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_two_gpu_sharded_step_matches_single_gpu_and_oracle(tmp_path, default_params):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import particle_3d as p3
+    from particle_3d import _abi
+    from oracle import oracle as O
+    from helpers import parity_errors
+
+    script = tmp_path / "worker.py"
+    script.write_text(f"ROOT = {ROOT!r}\nOUT = {str(tmp_path)!r}\n" + WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    W, n = 30.0, 27000
+    prm = dict(default_params, world_size=W)
+    ref = p3.generate_particles(W, n, seed=42)
+    for _ in range(3):
+        ref = O.update(prm, 1 / 60, ref, mode=O.IDEAL)["out"]
+    a, b = np.load(tmp_path / "shard_0.npy"), np.load(tmp_path / "shard_1.npy")
+    # after the final all-gather both ranks hold every position; velocities only for their own shard,
+    # so compare positions on both and velocities where each rank owns the slot (non-zero update)
+    for got in (a, b):
+        dv, dp = parity_errors(got, ref, W)
+        assert dp.max() < 5e-5
+    dva, _ = parity_errors(a, ref, W)
+    dvb, _ = parity_errors(b, ref, W)
+    assert np.minimum(dva, dvb).max() < 5e-5  # every particle's velocity is right on its owner rank
