@@ -79,7 +79,7 @@ struct p3d_engine {
     size_t n = 0;        // live particles
     int n_slots = 0;     // padded slots (multiple of B)
     int B = 128;         // block size in particles (32 * R) of the current layout
-    int B_next = 128;    // block size for the next upload (P3D_OPT_BLOCK_SIZE)
+    int B_next = 0;      // block size for the next upload (P3D_OPT_BLOCK_SIZE); 0 = by particle count
     int M = 0;           // n_slots / B
     uint32_t T = 0;      // id_count the layout was built for
     std::vector<int> seg_start_h, seg_end_h;
@@ -106,6 +106,7 @@ struct p3d_engine {
     int opt_timing = 0;
     int opt_graph = 0;
     int opt_block_sort = 1;
+    int opt_tune = 0;        // developer knob: kernel variant selection for experiments
 
     // sharding
     int rank = 0, world = 1;
@@ -171,7 +172,7 @@ int ensure_pinned(p3d_engine *e, size_t bytes) {
 // Builds the type-sorted slot layout for `n` particles with ids `in[i].id` and uploads it.
 int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T) {
     if (n > (size_t)0x7fff0000) return fail(P3D_ERR_INVALID, "n too large");
-    e->B = e->B_next;
+    e->B = e->B_next ? e->B_next : (n >= 65536 ? 256 : 128);
     const int B = e->B;
     std::vector<size_t> count(T, 0);
     for (size_t i = 0; i < n; ++i) {
@@ -320,27 +321,38 @@ int launch_force(p3d_engine *e, const DevParams &P) {
     const int M = e->M;
     const int rows = (M - e->rank + e->world - 1) / e->world;  // rows rank, rank+world, ...
     if (rows > 0) {
-        const int nw = 4;
+        // One warp per CTA: every per-block-pair scalar is then provably warp-uniform and lives in
+        // uniform registers (no register-file reads in the FFMA2 stream).  ~24 waves of 16 CTAs/SM
+        // keep the tail of the last wave small; never more warps than offsets in a row.
         const int offsets = M / 2 + 1;
-        // enough CTAs for ~8 waves of 4 CTAs/SM, but never more warps than offsets in a row
-        int splits = (int)std::min<long long>((offsets + nw - 1) / nw,
-                                              std::max<long long>(1, (8LL * 4 * e->sm_count + rows - 1) / rows));
-        if (splits < 1) splits = 1;
+        int splits = (int)std::min<long long>(offsets, std::max<long long>(1, (24LL * 16 * e->sm_count + rows - 1) / rows));
         const dim3 grid((unsigned)rows * (unsigned)splits);
         const float *sx = e->sx.p, *sy = e->sy.p, *sz = e->sz.p;
 #define P3D_PAIR_ARGS sx, sy, sz, e->sidx.p, e->bclass.p, e->seg_type.p, M, e->rank, e->world, splits, e->frc.p, P, e->matrix.p, flag_cur
         if (B == 128) {
-            if (P.rcut) k_force_pair<4, true><<<grid, nw * 32, 0, st>>>(P3D_PAIR_ARGS);
-            else        k_force_pair<4, false><<<grid, nw * 32, 0, st>>>(P3D_PAIR_ARGS);
+            if (P.rcut) k_force_pair<4, true, 16, 1><<<grid, 32, 0, st>>>(P3D_PAIR_ARGS);
+            else        k_force_pair<4, false, 16, 1><<<grid, 32, 0, st>>>(P3D_PAIR_ARGS);
         } else {
-            if (P.rcut) k_force_pair<8, true><<<grid, nw * 32, 0, st>>>(P3D_PAIR_ARGS);
-            else        k_force_pair<8, false><<<grid, nw * 32, 0, st>>>(P3D_PAIR_ARGS);
+            if (P.rcut) k_force_pair<8, true, 16, 1><<<grid, 32, 0, st>>>(P3D_PAIR_ARGS);
+            else        k_force_pair<8, false, 16, 1><<<grid, 32, 0, st>>>(P3D_PAIR_ARGS);
         }
 #undef P3D_PAIR_ARGS
         if (e->step_ev) CU(cudaEventRecord(e->step_ev[2], st));
+        // boundary x boundary: split the j-blocks of a row over enough CTAs to fill the machine
+        // (only BOUNDARY rows do work; their number is known on the device only, so estimate it from the
+        //  boundary shell volume of a uniform cloud — a clustered cloud has fewer and merely over-splits)
+        const double shell = 1.0 - std::pow(std::max(0.0, 1.0 - 2.0 * (double)P.reach / (double)P.W), 3.0);
+        const long long est_rows = std::max<long long>(P.T, (long long)(shell * rows) + P.T);
+        const int jsplit = (int)std::max<long long>(1, std::min<long long>(64, (8LL * e->sm_count + est_rows - 1) / est_rows));
+        const dim3 bgrid((unsigned)rows, (unsigned)jsplit);
 #define P3D_BXB_ARGS e->spos.p, e->sidx.p, e->bclass.p, M, e->rank, e->world, e->seg_start.p, e->seg_end.p, e->cnt.p, e->frc.p, P, e->matrix.p, flag_cur
-        if (B == 128) k_force_bxb<128><<<rows, 128, ref_smem(128, P.T), st>>>(P3D_BXB_ARGS);
-        else          k_force_bxb<256><<<rows, 256, ref_smem(256, P.T), st>>>(P3D_BXB_ARGS);
+        if (B == 128) {
+            if (P.rcut) k_force_bxb<128, true><<<bgrid, 128, ref_smem(128, P.T), st>>>(P3D_BXB_ARGS);
+            else        k_force_bxb<128, false><<<bgrid, 128, ref_smem(128, P.T), st>>>(P3D_BXB_ARGS);
+        } else {
+            if (P.rcut) k_force_bxb<256, true><<<bgrid, 256, ref_smem(256, P.T), st>>>(P3D_BXB_ARGS);
+            else        k_force_bxb<256, false><<<bgrid, 256, ref_smem(256, P.T), st>>>(P3D_BXB_ARGS);
+        }
 #undef P3D_BXB_ARGS
         e->counters[0] += 2;
         e->counters[1] += 2;
@@ -497,8 +509,9 @@ int p3d_set_option(p3d_engine *e, int option, int value) {
         case P3D_OPT_TIMING: e->opt_timing = value ? 1 : 0; return P3D_OK;
         case P3D_OPT_GRAPH: e->opt_graph = value ? 1 : 0; return P3D_OK;
         case P3D_OPT_BLOCK_SORT: e->opt_block_sort = value ? 1 : 0; return P3D_OK;
+        case 99: e->opt_tune = value; return P3D_OK;
         case P3D_OPT_BLOCK_SIZE:
-            if (value != 128 && value != 256) return fail(P3D_ERR_INVALID, "block size must be 128 or 256");
+            if (value != 0 && value != 128 && value != 256) return fail(P3D_ERR_INVALID, "block size must be 0 (auto), 128 or 256");
             e->B_next = value;
             return P3D_OK;
         default: return fail(P3D_ERR_INVALID, "unknown option %d", option);

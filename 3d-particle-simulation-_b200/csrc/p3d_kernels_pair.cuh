@@ -253,8 +253,8 @@ __device__ __forceinline__ void atomic_add_f3(float4 *dst, float x, float y, flo
 // K1 (fast): symmetric block-pair force pass.  grid.x = n_rows * splits, block = NW warps.
 // Row a (row_begin + k*row_stride: the multi-GPU shard takes every world-th row) owns the block
 // pairs {a, a+o mod M}, o in [0, M/2]; the warps of the `splits` CTAs of a row interleave over o.
-template <int R, bool RCUT>
-__global__ void __launch_bounds__(128, 4)
+template <int R, bool RCUT, int MINB, int NW>
+__global__ void __launch_bounds__(32 * NW, MINB)
 k_force_pair(const float *__restrict__ sx, const float *__restrict__ sy, const float *__restrict__ sz,
              const uint32_t *__restrict__ sidx,
              const uint8_t *__restrict__ bclass, const uint8_t *__restrict__ btype, int M, int row_begin,
@@ -264,8 +264,10 @@ k_force_pair(const float *__restrict__ sx, const float *__restrict__ sy, const f
     constexpr int B = 32 * R;
     constexpr int ROUNDS = B / 64;
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int nw = blockDim.x >> 5;
+    // NW == 1: one warp per CTA makes every per-block-pair quantity (b, types, matrix entries)
+    // provably warp-uniform for the compiler, so it can live in uniform registers
+    const int warp = (NW == 1) ? 0 : (threadIdx.x >> 5);
+    constexpr int nw = NW;
     const int row = row_begin + (blockIdx.x / splits) * row_stride;
     const int split = blockIdx.x % splits;
     if (row >= M) return;
@@ -328,10 +330,21 @@ k_force_pair(const float *__restrict__ sx, const float *__restrict__ sy, const f
     }
 }
 
-// K1 (boundary x boundary): ordered pairs between BOUNDARY-class blocks, with the reference's exact
-// image arithmetic (three candidates per axis, rounding of position + offset, exact sqrt and divides).
-// One thread per i; the boundary blocks of each type are the tail of that type's region.
-template <int B>
+// Nearest of the two images of the i-particle that can be in range of an in-box q: offset 0 and
+// offset -sign(p)*W.  `pa` is the reference's rounded `position + offset` (src/lib.rs:190-192,211-212).
+__device__ __forceinline__ float nearest_image2(float q, float p0, float pa) {
+    const float r0 = __fsub_rn(q, p0), ra = __fsub_rn(q, pa);
+    return (fabsf(ra) < fabsf(r0)) ? ra : r0;
+}
+
+// K1 (boundary x boundary): ordered pairs between BOUNDARY-class blocks — the only pairs that can
+// interact through a periodic image.  One thread per i-particle, j-tiles of boundary blocks staged in
+// shared memory.  Relative positions follow the reference's image arithmetic exactly
+// (`other.position - (position + offset)` with the f32 rounding of position + offset); the force law
+// is the same branch-free rsqrt form as k_force_pair.  All particles are inside the box here (the
+// flag check), so per axis only offsets 0 and -sign(p)*W can be within reach.
+// grid = (rows of this shard, jsplit): CTA (x, y) takes every jsplit-th boundary block.
+template <int B, bool RCUT>
 __global__ void __launch_bounds__(B) k_force_bxb(const float4 *__restrict__ spos, const uint32_t *__restrict__ sidx,
                                                  const uint8_t *__restrict__ bclass, int M, int row_begin,
                                                  int row_stride, const int *__restrict__ seg_start,
@@ -349,36 +362,47 @@ __global__ void __launch_bounds__(B) k_force_bxb(const float4 *__restrict__ spos
     const float4 pi = spos[row * B + threadIdx.x];
     const uint32_t idi = f2u(pi.w);
     const bool live = idi != P3D_GHOST_ID;
-    const float pxm = __fadd_rn(pi.x, -P.W), pxp = __fadd_rn(pi.x, P.W);
-    const float pym = __fadd_rn(pi.y, -P.W), pyp = __fadd_rn(pi.y, P.W);
-    const float pzm = __fadd_rn(pi.z, -P.W), pzp = __fadd_rn(pi.z, P.W);
+    // position + offset for the one non-zero offset per axis that can matter
+    const float pxa = __fadd_rn(pi.x, pi.x > 0.f ? -P.W : P.W);
+    const float pya = __fadd_rn(pi.y, pi.y > 0.f ? -P.W : P.W);
+    const float pza = __fadd_rn(pi.z, pi.z > 0.f ? -P.W : P.W);
     const uint32_t mrow = live ? idi * (uint32_t)P.T : 0u;
+    const float c2 = P.c2, ncm = -P.c2 * P.m, nc2 = -P.c2, im = P.inv_m, r2 = P.r2;
     float ax = 0.f, ay = 0.f, az = 0.f;
+    int visit = 0;
     for (int t = 0; t < P.T; ++t) {
         const int hi = seg_end[t] - cnt[2 * t + 1];  // first boundary entry of type t
-        const int b_first = hi / B;                  // the block holding it (BOUNDARY or EMPTY if none)
+        const int b_first = hi / B;                  // the block holding it
         const int b_last = seg_end[t] / B;
         for (int b = b_first; b < b_last; ++b) {
             if (bclass[b] != P3D_BLK_BOUNDARY) continue;
+            if ((visit++ % (int)gridDim.y) != (int)blockIdx.y) continue;
             __syncthreads();
             tile[threadIdx.x] = spos[b * B + threadIdx.x];
             __syncthreads();
             if (!live) continue;
+            const float *arow = smat + mrow;
 #pragma unroll 4
             for (int k = 0; k < B; ++k) {
                 const float4 q = tile[k];
-                const float rx = nearest_image3(q.x, pi.x, pxm, pxp);
-                const float ry = nearest_image3(q.y, pi.y, pym, pyp);
-                const float rz = nearest_image3(q.z, pi.z, pzm, pzp);
-                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
-                if (d2 > 0.0f && d2 < P.r2) {
-                    const float d = __fsqrt_rn(d2);
-                    const float a = smat[mrow + f2u(q.w)];
-                    const float f = ref_calculate_force(P.m, d, a);
-                    ax = __fadd_rn(ax, __fmul_rn(__fdiv_rn(rx, d), f));
-                    ay = __fadd_rn(ay, __fmul_rn(__fdiv_rn(ry, d), f));
-                    az = __fadd_rn(az, __fmul_rn(__fdiv_rn(rz, d), f));
+                const float rx = nearest_image2(q.x, pi.x, pxa);
+                const float ry = nearest_image2(q.y, pi.y, pya);
+                const float rz = nearest_image2(q.z, pi.z, pza);
+                const float d2 = fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, 1.0e-30f)));
+                const float inv = rsqrt_approx(d2);
+                const float p1 = fmaf(inv, ncm, c2), p2 = fmaf(inv, c2, nc2);
+                float ti = fmaxf(fminf(p1, p2), 0.0f);
+                float rs = fminf(im - inv, 0.0f);
+                if (RCUT) {
+                    if (!(d2 < r2)) { ti = 0.0f; rs = 0.0f; }
                 }
+                // ghosts (type id 0xFFFFFFFF) sit 1e15 away: ti = rs = 0, so any matrix entry will do
+                const uint32_t tj = f2u(q.w);
+                const float a = arow[tj < (uint32_t)P.T ? tj : 0u];
+                const float s = fmaf(a, ti, rs);
+                ax = fmaf(rx, s, ax);
+                ay = fmaf(ry, s, ay);
+                az = fmaf(rz, s, az);
             }
         }
     }

@@ -165,10 +165,61 @@ __global__ void __launch_bounds__(128) mb_generic(float *out, int iters, float a
     if (acc == 123.456f) out[0] = acc;
 }
 
+// Register-file operand-bandwidth probes for FFMA2.  OPS: 0: d = a*b + d, three distinct register
+// pairs; 1: d = a*a + d, two distinct pairs; 2: d = a*s + d with s a broadcast scalar register;
+// 3: as 0 but consecutive instructions share `b` (operand-reuse cache); 4: 12 FFMA2 + 12 scalar FFMA
+// on disjoint data (does the scalar FFMA find a free FMA datapath beside FFMA2?).
+template <int OPS>
+__global__ void __launch_bounds__(128) mb_rf(float *out, int iters, float a, float b) {
+    constexpr int CH = 8;
+    float2 d[CH], x[CH], y[CH];
+    float g[12];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        d[k] = make_float2((float)(threadIdx.x + k), (float)k);
+        x[k] = make_float2(a + 1e-3f * (threadIdx.x + k), a - 1e-3f * k);
+        y[k] = make_float2(b + 1e-3f * (threadIdx.x + 2 * k), b - 2e-3f * k);
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) g[k] = (float)(threadIdx.x + k);
+    const float sc = a + 1e-4f * threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep) {
+            if (OPS == 0) {
+#pragma unroll
+                for (int k = 0; k < CH; ++k) d[k] = __ffma2_rn(x[k], y[(k + rep) % CH], d[k]);
+            } else if (OPS == 1) {
+#pragma unroll
+                for (int k = 0; k < CH; ++k) d[k] = __ffma2_rn(x[(k + rep) % CH], x[(k + rep) % CH], d[k]);
+            } else if (OPS == 2) {
+#pragma unroll
+                for (int k = 0; k < CH; ++k) d[k] = __ffma2_rn(x[(k + rep) % CH], make_float2(sc, sc), d[k]);
+            } else if (OPS == 3) {
+#pragma unroll
+                for (int k = 0; k < CH; ++k) d[k] = __ffma2_rn(x[k], y[rep % CH], d[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < CH; ++k) d[k] = __ffma2_rn(d[k], make_float2(a, a), make_float2(b, b));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d[k] = __ffma2_rn(d[k], make_float2(a, a), make_float2(b, b));
+#pragma unroll
+                for (int k = 0; k < 12; ++k) g[k] = fmaf(g[k], a, b);
+            }
+        }
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc += d[k].x + d[k].y;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc += g[k];
+    if (acc == 123.456f) out[0] = acc;
+}
+
 }  // namespace
 
 extern "C" int p3d_microbench(int device, int kind, int iters, double out[4]) {
-    if (!out || iters <= 0 || kind < 0 || kind > 12) return P3D_ERR_INVALID;
+    if (!out || iters <= 0 || kind < 0 || kind > 17) return P3D_ERR_INVALID;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
         cudaGetLastError();
@@ -192,6 +243,7 @@ extern "C" int p3d_microbench(int device, int kind, int iters, double out[4]) {
     if (kind == 2) { threads = 128; ctas_per_sm = 4; lane_fma_per_thread = (double)iters * 8 * 4 * 17 * 2; }
     if (kind == 3) { threads = 128; ctas_per_sm = 4; lane_fma_per_thread = (double)iters * 8 * 68 * 2; }
     if (kind >= 4) { threads = 128; ctas_per_sm = 4; lane_fma_per_thread = (double)iters * 16; }  // bodies per thread
+    if (kind >= 13) lane_fma_per_thread = (double)iters * 8;  // reps per thread (8 FFMA2 each; kind 17: 12 FFMA2 + 12 FFMA)
     const int grid = sms * ctas_per_sm;
     for (int rep = 0; rep < 2; ++rep) {  // first launch warms up
         cudaEventRecord(e0);
@@ -208,6 +260,11 @@ extern "C" int p3d_microbench(int device, int kind, int iters, double out[4]) {
         if (kind == 9) mb_generic<0, 34, 6, 2, 0><<<grid, threads>>>(d, iters, 0.999f, 0.001f);   // scalar mix
         if (kind == 10) mb_generic<17, 0, 6, 2, 0><<<grid, threads>>>(d, iters, 0.999f, 0.001f);  // packed mix
         if (kind == 11) mb_generic<17, 0, 6, 2, 3><<<grid, threads>>>(d, iters, 0.999f, 0.001f);  // packed mix + SHFL
+        if (kind == 13) mb_rf<0><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 14) mb_rf<1><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 15) mb_rf<2><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 16) mb_rf<3><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 17) mb_rf<4><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
         if (kind == 12) mb_generic<17, 0, 0, 0, 0><<<grid, threads>>>(d, iters, 0.999f, 0.001f);  // FFMA2 only
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return P3D_ERR_CUDA; }

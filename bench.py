@@ -356,7 +356,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--n", type=int, default=N_DEFAULT)
     ap.add_argument("--world-size", type=float, default=None, help="box edge W (default: density 1)")
-    ap.add_argument("--block", type=int, default=256, choices=[128, 256])
+    ap.add_argument("--block", type=int, default=0, choices=[0, 128, 256], help="0 = engine default")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu", action="store_true")

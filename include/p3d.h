@@ -89,7 +89,7 @@ enum p3d_option {
     P3D_OPT_TIMING = 1,       /* 1: record CUDA events around each kernel of a step */
     P3D_OPT_GRAPH = 2,        /* 1: replay p3d_step through a CUDA graph */
     P3D_OPT_BLOCK_SORT = 3,   /* 1: re-partition interior/boundary blocks every step (fast path) */
-    P3D_OPT_BLOCK_SIZE = 4    /* particles per block of the pair kernel: 128 (R=4) or 256 (R=8); applies at the next upload */
+    P3D_OPT_BLOCK_SIZE = 4    /* particles per block of the pair kernel: 0 = auto (256 from 65,536 particles, else 128), 128 (R=4) or 256 (R=8); applies at the next upload */
 };
 enum p3d_force_kernel {
     P3D_FORCE_AUTO = 0,      /* PAIR for n >= 4096, else REFERENCE_ORDER */
@@ -138,6 +138,7 @@ int p3d_shard_commit(p3d_engine *eng);
 /* ---- FP32-pipe microbenchmarks: make the roofline denominator defensible ----
  * kind 0: dependent-chain-free scalar FFMA; 1: packed FFMA2; 2: the pair kernel's instruction mix
  * (17 FFMA2/FADD2 : 2 MUFU.RSQ : 6 FMNMX); 3: FFMA2 with the pair kernel's shuffle rate (12 SHFL per 68 FFMA2).
+ * kinds 4..17 are instruction-mix and register-operand-bandwidth probes used in DESIGN.md §5 (out[0] = thread-bodies/s).
  * out[0] = FP32 lane-FMAs per second (an FFMA2 counts 2 per lane), out[1] = kernel ms,
  * out[2] = SM count, out[3] = max SM clock in MHz as reported by the driver. */
 int p3d_microbench(int device, int kind, int iters, double out[4]);

@@ -28,7 +28,7 @@ def eng():
     e.close()
 
 
-def gpu_update(eng, prm, parts, kernel, ts=TS, block=128):
+def gpu_update(eng, prm, parts, kernel, ts=TS, block=0):
     eng.set_option(_abi.OPT_FORCE_KERNEL, kernel)
     eng.set_option(_abi.OPT_BLOCK_SIZE, block)
     return eng.update(p3.Engine.make_params(**prm), ts, parts)

@@ -15,7 +15,7 @@ from particle_3d import _abi
 from oracle import oracle as O
 
 
-def parity(n, W, kernel, steps=1, seed=42, plummer=False, block=128, **over):
+def parity(n, W, kernel, steps=1, seed=42, plummer=False, block=0, **over):
     prm = p3.default_params_dict()
     prm["world_size"] = W
     prm.update(over)
@@ -62,7 +62,7 @@ class Clocks:
                             power_max=max(pw) if pw else None, reasons=sorted(set(r[3] for r in rows)))
 
 
-def timing(n, W, kernel, steps=3, plummer=False, block=128):
+def timing(n, W, kernel, steps=3, plummer=False, block=0, tune=0):
     prm = p3.default_params_dict()
     prm["world_size"] = W
     parts = p3.generate_plummer(W, n, W / 6, 42) if plummer else p3.generate_particles(W, n, 42)
@@ -70,6 +70,7 @@ def timing(n, W, kernel, steps=3, plummer=False, block=128):
     eng.set_option(_abi.OPT_FORCE_KERNEL, kernel)
     eng.set_option(_abi.OPT_TIMING, 1)
     eng.set_option(_abi.OPT_BLOCK_SIZE, block)
+    eng.set_option(99, tune)
     P = p3.Engine.make_params(**prm)
     eng.upload(parts, 5)
     eng.step(P, 1 / 60, 1)
@@ -85,7 +86,7 @@ def timing(n, W, kernel, steps=3, plummer=False, block=128):
     pairs = float(n) * n
     print(f"timing n={n} kernel={kernel}: force {f_ms:.3f} ms  integrate {i_ms*1e3:.1f} us  wall/step {wall*1e3:.3f} ms  "
           f"{pairs/f_ms/1e9:.2f} T interactions/s  = {pairs*20/(f_ms*1e-3)/74.5e12*100:.1f}% of 74.5 TF  "
-          f"integrate {80*n/i_ms/1e6:.0f} GB/s  B={block}  clocks={ck.summary}", flush=True)
+          f"integrate {80*n/i_ms/1e6:.0f} GB/s  B={block} tune={tune} pair={t["pair"]/steps:.3f}ms bxb={t["bxb"]/steps:.3f}ms part={t["partition"]/steps*1e3:.0f}us  clocks={ck.summary}", flush=True)
     eng.close()
 
 
@@ -111,8 +112,21 @@ def micro2():
         print(f"micro2 [{names[kind]}]: rc={rc} {out[1]:.2f} ms -> {cyc:.1f} SMSP-cycles per warp-body (at max clock)", flush=True)
 
 
+def micro3():
+    L = _abi.load()
+    names = {13: "8 FFMA2 d=a*b+d (3 distinct pairs)", 14: "8 FFMA2 d=a*a+d (2 distinct)", 15: "8 FFMA2 d=a*s+d (pair, scalar, pair)",
+             16: "8 FFMA2 d=a*b+d, b shared by consecutive instrs", 17: "12 FFMA2 + 12 FFMA (disjoint)"}
+    for kind in sorted(names):
+        out = (C.c_double * 4)()
+        rc = L.p3d_microbench(0, kind, 4000, out)
+        cyc = out[3] * 1e6 * out[2] * 4 / (out[0] / 32)
+        print(f"micro3 [{names[kind]}]: rc={rc} {out[1]:.2f} ms -> {cyc:.2f} SMSP-cycles per body", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["parity", "timing", "micro"]
+    if "micro3" in what:
+        micro3()
     if "micro" in what:
         micro()
         micro2()
@@ -126,6 +140,9 @@ if __name__ == "__main__":
         parity(16384, 25.4, _abi.FORCE_PAIR, walls=True, acceleration=(0.0, -1.0, 0.0))
         parity(16384, 25.4, _abi.FORCE_PAIR, particle_effect_radius=0.8)
         parity(20000, 64.0, _abi.FORCE_PAIR, plummer=True)
+    if "tune" in what:
+        for blk, tune in ((128, 0), (256, 0)):
+            timing(262144, 64.0, _abi.FORCE_PAIR, steps=4, block=blk, tune=tune)
     if "timing" in what:
         timing(1000, 10.0, _abi.FORCE_REFERENCE_ORDER, steps=20)
         timing(16384, 25.4, _abi.FORCE_REFERENCE_ORDER, steps=5)
