@@ -15,6 +15,9 @@
 #include "p3d.h"
 #include "p3d_kernels_basic.cuh"
 #include "p3d_kernels_pair.cuh"
+#include "p3d_kernels_cells.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
 
 static_assert(sizeof(p3d_particle) == 28, "boundary struct must be 28 bytes (src/lib.rs:12-17)");
 static_assert(sizeof(AosParticle) == 28, "device view of the boundary struct");
@@ -89,6 +92,10 @@ struct p3d_engine {
     DevBuf<uint8_t> seg_type, bclass;
     DevBuf<int> seg_start, seg_end, cnt;
     DevBuf<int2> cta_cnt, cta_off;
+    // cell-list path
+    DevBuf<uint32_t> ckeys[2], cvals[2], cell_start, cell_end;
+    DevBuf<float4> cpos;
+    DevBuf<unsigned char> cub_tmp;
     DevBuf<float> aos, fout, sx, sy, sz;
     DevBuf<float> matrix;
     DevBuf<int> flags;      // [0],[1]: out-of-box flags (double-buffered by step parity)
@@ -302,6 +309,69 @@ int launch_force(p3d_engine *e, const DevParams &P) {
         CU(cudaGetLastError());
         return P3D_OK;
     }
+    if (kind == P3D_FORCE_CELLS) {
+        // cells of edge W/nc >= reach; at most ~8 cells per particle so sparse scenes stay cheap
+        const float reach = P.reach * 1.001f + 1.0e-4f;
+        long long nc = (long long)std::floor((double)P.W / (double)reach);
+        const long long cap = (long long)std::cbrt(8.0 * (double)std::max<size_t>(e->n, 64)) + 1;
+        nc = std::min<long long>(std::min<long long>(nc, cap), 1024);
+        if (nc >= 3) {
+            const size_t ncell = (size_t)(nc * nc * nc);
+            int rc;
+            for (int k = 0; k < 2; ++k) {
+                if ((rc = e->ckeys[k].ensure((size_t)ns))) return rc;
+                if ((rc = e->cvals[k].ensure((size_t)ns))) return rc;
+            }
+            if ((rc = e->cpos.ensure((size_t)ns))) return rc;
+            if ((rc = e->cell_start.ensure(ncell + 1))) return rc;
+            if ((rc = e->cell_end.ensure(ncell + 1))) return rc;
+            int end_bit = 1;
+            while ((1ull << end_bit) <= ncell) ++end_bit;
+            size_t tmp_bytes = 0;
+            CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, e->ckeys[0].p, e->ckeys[1].p, e->cvals[0].p,
+                                               e->cvals[1].p, ns, 0, end_bit, st));
+            if ((rc = e->cub_tmp.ensure(tmp_bytes))) return rc;
+            CellGrid g;
+            g.nc = (int)nc;
+            g.inv_cs = (float)((double)nc / (double)P.W);
+            g.half = P.half;
+            CU(cudaMemsetAsync(e->cell_start.p, 0xFF, (ncell + 1) * sizeof(uint32_t), st));
+            k_cell_keys<<<(ns + 255) / 256, 256, 0, st>>>(pos, ns, g, e->ckeys[0].p, e->cvals[0].p, flag_next);
+            CU(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp_bytes, e->ckeys[0].p, e->ckeys[1].p, e->cvals[0].p,
+                                               e->cvals[1].p, ns, 0, end_bit, st));
+            k_cell_gather<<<(ns + 255) / 256, 256, 0, st>>>(pos, ns, e->ckeys[1].p, e->cvals[1].p, e->cpos.p,
+                                                           e->cell_start.p, e->cell_end.p);
+            if (e->step_ev) CU(cudaEventRecord(e->step_ev[1], st));
+            if (e->world > 1) CU(cudaMemsetAsync(e->frc.p, 0, (size_t)ns * sizeof(float4), st));
+            const int per = (ns + e->world - 1) / e->world;
+            const int i0 = std::min(ns, e->rank * per), i1 = std::min(ns, i0 + per);
+            if (i1 > i0) {
+                const size_t sm = (size_t)P.T * P.T * sizeof(float);
+                if (P.rcut)
+                    k_force_cells<true><<<(i1 - i0 + 127) / 128, 128, sm, st>>>(
+                        e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_start.p, e->cell_end.p, ns, i0, i1, g,
+                        e->frc.p, P, e->matrix.p, flag_cur);
+                else
+                    k_force_cells<false><<<(i1 - i0 + 127) / 128, 128, sm, st>>>(
+                        e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_start.p, e->cell_end.p, ns, i0, i1, g,
+                        e->frc.p, P, e->matrix.p, flag_cur);
+            }
+            e->counters[0] += 4;
+            e->counters[1] += 1;
+            if (e->step_ev) CU(cudaEventRecord(e->step_ev[2], st));
+            // out-of-box inputs (flag set): the reference-order kernel takes the whole step instead
+            const int perb = ((e->M + e->world - 1) / e->world) * e->B;
+            const int r0 = std::min(ns, e->rank * perb), r1 = std::min(ns, r0 + perb);
+            if (r1 > r0) {
+                k_force_ref<kRefTile><<<(r1 - r0 + kRefTile - 1) / kRefTile, kRefTile, ref_smem(kRefTile, P.T), st>>>(
+                    pos, ns, r0, r1, e->frc.p, P, e->matrix.p, flag_cur, 1);
+                e->counters[0]++;
+            }
+            CU(cudaGetLastError());
+            return P3D_OK;
+        }
+        // box narrower than three cells: the all-pairs path below handles it
+    }
     // --- pair path ---
     const int B = e->B;
     const float margin = std::max(1.0e-3f, 1.0e-5f * P.W);
@@ -485,6 +555,9 @@ void p3d_destroy(p3d_engine *e) {
     e->perm.release(); e->slot_of.release(); e->sidx.release();
     e->seg_type.release(); e->bclass.release();
     e->seg_start.release(); e->seg_end.release(); e->cnt.release(); e->cta_cnt.release(); e->cta_off.release();
+    for (auto &b : e->ckeys) b.release();
+    for (auto &b : e->cvals) b.release();
+    e->cell_start.release(); e->cell_end.release(); e->cpos.release(); e->cub_tmp.release();
     e->aos.release(); e->fout.release(); e->sx.release(); e->sy.release(); e->sz.release(); e->matrix.release(); e->flags.release(); e->diag.release();
     if (e->pin) cudaFreeHost(e->pin);
     for (auto x : e->ev) cudaEventDestroy(x);
@@ -503,7 +576,7 @@ int p3d_set_option(p3d_engine *e, int option, int value) {
     if (!e) return fail(P3D_ERR_INVALID, "engine is null");
     switch (option) {
         case P3D_OPT_FORCE_KERNEL:
-            if (value < P3D_FORCE_AUTO || value > P3D_FORCE_PAIR) return fail(P3D_ERR_INVALID, "bad force kernel %d", value);
+            if (value < P3D_FORCE_AUTO || value > P3D_FORCE_CELLS) return fail(P3D_ERR_INVALID, "bad force kernel %d", value);
             e->opt_force = value;
             return P3D_OK;
         case P3D_OPT_TIMING: e->opt_timing = value ? 1 : 0; return P3D_OK;

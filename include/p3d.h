@@ -94,7 +94,9 @@ enum p3d_option {
 enum p3d_force_kernel {
     P3D_FORCE_AUTO = 0,      /* PAIR for n >= 4096, else REFERENCE_ORDER */
     P3D_FORCE_REFERENCE_ORDER = 1, /* one thread per particle, exact sqrt/div, all three images per axis */
-    P3D_FORCE_PAIR = 2       /* symmetric block-pair kernel, packed FP32x2, rsqrt */
+    P3D_FORCE_PAIR = 2,      /* symmetric block-pair kernel, packed FP32x2, rsqrt (all N^2 pairs) */
+    P3D_FORCE_CELLS = 3      /* uniform-grid cell list: the GPU analogue of the reference's spatial hash
+                                (src/lib.rs:135-236); same results, O(N * neighbours) work */
 };
 int p3d_set_option(p3d_engine *eng, int option, int value);
 int p3d_get_option(p3d_engine *eng, int option, int *value);

@@ -17,8 +17,8 @@ from helpers import assert_parity, parity_errors, pos, vel
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TS = float(np.float32(1.0 / 60.0))
-KERNELS = [_abi.FORCE_REFERENCE_ORDER, _abi.FORCE_PAIR]
-IDS = ["reference_order", "pair"]
+KERNELS = [_abi.FORCE_REFERENCE_ORDER, _abi.FORCE_PAIR, _abi.FORCE_CELLS]
+IDS = ["reference_order", "pair", "cells"]
 
 
 @pytest.fixture(scope="module")
@@ -90,6 +90,8 @@ def test_config2_16k_uniform(eng, default_params, block):
     assert_parity(out, ref, W, what=f"config 2 block={block}")
     out2 = gpu_update(eng, prm, start, _abi.FORCE_REFERENCE_ORDER)
     assert_parity(out2, ref, W, what="config 2 reference-order kernel")
+    out3 = gpu_update(eng, prm, start, _abi.FORCE_CELLS)
+    assert_parity(out3, ref, W, what="config 2 cell-list kernel")
 
 
 def test_plummer_cluster_one_step(eng, default_params):
@@ -98,6 +100,7 @@ def test_plummer_cluster_one_step(eng, default_params):
     start = p3.generate_plummer(W, 30000, W / 6, seed=42)
     ref = O.update(prm, TS, start, mode=O.IDEAL)["out"]
     assert_parity(gpu_update(eng, prm, start, _abi.FORCE_PAIR), ref, W, what="plummer")
+    assert_parity(gpu_update(eng, prm, start, _abi.FORCE_CELLS), ref, W, what="plummer, cell list")
 
 
 # ---------------------------------------------------------------- hand-derived known answers
@@ -282,6 +285,8 @@ def test_pair_kernel_agrees_with_reference_order_kernel_at_262k(eng, default_par
     a = gpu_update(eng, prm, start, _abi.FORCE_PAIR)
     b = gpu_update(eng, prm, start, _abi.FORCE_REFERENCE_ORDER)
     assert_parity(a, b, W, what="pair vs reference-order at 262k")
+    c = gpu_update(eng, prm, start, _abi.FORCE_CELLS)
+    assert_parity(c, b, W, what="cell list vs reference-order at 262k")
 
 
 def test_newton_third_law_with_symmetric_matrix_at_1m(eng, default_params):
@@ -303,6 +308,13 @@ def test_newton_third_law_with_symmetric_matrix_at_1m(eng, default_params):
     frms = np.sqrt((ref ** 2).sum(1).mean())
     err = np.linalg.norm(f - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), frms)
     assert err.max() < 1e-5
+    # the cell-list path on the same full-size input
+    eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_CELLS)
+    eng.upload(start, 5)
+    eng.step(p3.Engine.make_params(**prm), TS, 1)
+    fc = eng.download_forces().astype(np.float64)
+    errc = np.linalg.norm(fc - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), frms)
+    assert errc.max() < 1e-5
 
 
 # ---------------------------------------------------------------- sharding, emulated on one GPU

@@ -140,6 +140,13 @@ if __name__ == "__main__":
         parity(16384, 25.4, _abi.FORCE_PAIR, walls=True, acceleration=(0.0, -1.0, 0.0))
         parity(16384, 25.4, _abi.FORCE_PAIR, particle_effect_radius=0.8)
         parity(20000, 64.0, _abi.FORCE_PAIR, plummer=True)
+    if "cells" in what:
+        timing(1000, 10.0, _abi.FORCE_CELLS, steps=50)
+        timing(16384, 25.4, _abi.FORCE_CELLS, steps=50)
+        timing(262144, 64.0, _abi.FORCE_CELLS, steps=20)
+        timing(262144, 64.0, _abi.FORCE_CELLS, steps=20, plummer=True)
+        timing(1048576, 101.6, _abi.FORCE_CELLS, steps=20)
+        timing(4194304, 161.3, _abi.FORCE_CELLS, steps=10)
     if "tune" in what:
         for blk, tune in ((128, 0), (256, 0)):
             timing(262144, 64.0, _abi.FORCE_PAIR, steps=4, block=blk, tune=tune)
