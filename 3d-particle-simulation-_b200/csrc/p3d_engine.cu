@@ -85,6 +85,7 @@ struct p3d_engine {
     int B_next = 0;      // block size for the next upload (P3D_OPT_BLOCK_SIZE); 0 = by particle count
     int M = 0;           // n_slots / B
     uint32_t T = 0;      // id_count the layout was built for
+    bool typed = false;  // slots are grouped by type (needed by the pair kernel); false: slot = caller index
     std::vector<int> seg_start_h, seg_end_h;
 
     DevBuf<float4> pos[2], vel, frc, spos;
@@ -177,8 +178,43 @@ int ensure_pinned(p3d_engine *e, size_t bytes) {
 }
 
 // Builds the type-sorted slot layout for `n` particles with ids `in[i].id` and uploads it.
+int ensure_common(p3d_engine *e, size_t n, size_t ns) {
+    int rc;
+    if ((rc = e->pos[0].ensure(ns))) return rc;
+    if ((rc = e->pos[1].ensure(ns))) return rc;
+    if ((rc = e->vel.ensure(ns))) return rc;
+    if ((rc = e->frc.ensure(ns))) return rc;
+    if ((rc = e->perm.ensure(ns))) return rc;
+    if ((rc = e->aos.ensure((n ? n : 1) * 7))) return rc;
+    if ((rc = e->matrix.ensure(P3D_MAX_TYPES * P3D_MAX_TYPES))) return rc;
+    if ((rc = e->flags.ensure(4))) return rc;
+    if ((rc = e->diag.ensure(8))) return rc;
+    return P3D_OK;
+}
+
+int resolve_force_kernel_for(const p3d_engine *e, size_t n);
+
+// Identity layout (slot = caller index): all the cell-list and reference-order kernels need.  No host
+// pass over the particles; ids are validated on the device by k_pack.
+int build_layout_identity(p3d_engine *e, size_t n, uint32_t T) {
+    if (n > (size_t)0x7fff0000) return fail(P3D_ERR_INVALID, "n too large");
+    e->B = 128;
+    const size_t unit = (size_t)e->B * (size_t)e->world;
+    const size_t ns = (std::max<size_t>(n, 1) + unit - 1) / unit * unit;
+    e->n_slots = (int)ns;
+    e->M = e->n_slots / e->B;
+    e->n = n;
+    e->T = T;
+    e->typed = false;
+    int rc;
+    if ((rc = ensure_common(e, n, ns))) return rc;
+    CU(cudaMemsetAsync(e->flags.p, 0, 4 * sizeof(int), e->stream));
+    return P3D_OK;
+}
+
 int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T) {
     if (n > (size_t)0x7fff0000) return fail(P3D_ERR_INVALID, "n too large");
+    e->typed = true;
     e->B = e->B_next ? e->B_next : (n >= 65536 ? 256 : 128);
     const int B = e->B;
     std::vector<size_t> count(T, 0);
@@ -258,8 +294,8 @@ int launch_pack(p3d_engine *e, size_t n) {
     k_fill_ghosts<<<(ns + 255) / 256, 256, 0, st>>>(e->pos[0].p, e->pos[1].p, e->vel.p, e->frc.p, e->perm.p, ns);
     e->counters[0]++;
     if (n) {
-        k_pack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->aos.p, e->slot_of.p, e->pos[0].p, e->vel.p,
-                                                            e->perm.p, (int)n);
+        k_pack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->aos.p, e->typed ? e->slot_of.p : nullptr, e->pos[0].p,
+                                                            e->vel.p, e->perm.p, (int)n, e->T, e->flags.p + 2);
         e->counters[0]++;
     }
     CU(cudaGetLastError());
@@ -268,17 +304,18 @@ int launch_pack(p3d_engine *e, size_t n) {
 
 int launch_unpack(p3d_engine *e, size_t n) {
     if (!n) return P3D_OK;
-    k_unpack<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->pos[e->cur].p, e->vel.p, e->slot_of.p, e->aos.p,
-                                                                 (int)n);
+    k_unpack<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->pos[e->cur].p, e->vel.p,
+                                                                 e->typed ? e->slot_of.p : nullptr, e->aos.p, (int)n);
     e->counters[0]++;
     CU(cudaGetLastError());
     return P3D_OK;
 }
 
-int resolve_force_kernel(const p3d_engine *e) {
-    if (e->opt_force == P3D_FORCE_AUTO) return e->n >= (size_t)kPairAutoMin ? P3D_FORCE_PAIR : P3D_FORCE_REFERENCE_ORDER;
+int resolve_force_kernel_for(const p3d_engine *e, size_t n) {
+    if (e->opt_force == P3D_FORCE_AUTO) return n >= (size_t)kPairAutoMin ? P3D_FORCE_PAIR : P3D_FORCE_REFERENCE_ORDER;
     return e->opt_force;
 }
+int resolve_force_kernel(const p3d_engine *e) { return resolve_force_kernel_for(e, e->n); }
 
 size_t ref_smem(int tile, int T) { return (size_t)tile * sizeof(float4) + (size_t)T * T * sizeof(float); }
 
@@ -373,6 +410,8 @@ int launch_force(p3d_engine *e, const DevParams &P) {
         // box narrower than three cells: the all-pairs path below handles it
     }
     // --- pair path ---
+    if (!e->typed)
+        return fail(P3D_ERR_INVALID, "the pair kernel needs the type-grouped layout: set the force kernel before p3d_upload");
     const int B = e->B;
     const float margin = std::max(1.0e-3f, 1.0e-5f * P.W);
     const float interior_limit = e->opt_block_sort ? (P.half - P.reach - margin) : -1.0f;
@@ -610,7 +649,11 @@ int p3d_upload(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t id_coun
         return fail(P3D_ERR_INVALID, "id_count %u outside 1..%d", id_count, P3D_MAX_TYPES);
     CU(cudaSetDevice(e->device));
     int rc;
-    if ((rc = build_layout(e, in, n, id_count))) return rc;
+    // The pair kernel needs type-grouped slots (host counting sort); every other kernel runs on the
+    // identity layout, which costs no host pass at all.
+    if (resolve_force_kernel_for(e, n) == P3D_FORCE_PAIR) rc = build_layout(e, in, n, id_count);
+    else rc = build_layout_identity(e, n, id_count);
+    if (rc) return rc;
     if (e->opt_timing) {
         if ((rc = ensure_events(e, 1))) return rc;
         CU(cudaEventRecord(e->ev_call[0], e->stream));
@@ -619,11 +662,19 @@ int p3d_upload(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t id_coun
     if (e->opt_timing) CU(cudaEventRecord(e->ev_call[1], e->stream));
     if ((rc = launch_pack(e, n))) return rc;
     if (e->opt_timing) CU(cudaEventRecord(e->ev_call[2], e->stream));
-    // `in` may be pageable: make sure the copy has consumed it before returning to the caller
+    // `in` may be pageable or reused by the caller: the copy must have consumed it before we return.
+    // The same sync brings back the device-side id check of the identity layout.
+    int bad_id = 0;
+    CU(cudaMemcpyAsync(&bad_id, e->flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     if (e->opt_timing) {
         CU(cudaEventElapsedTime(&e->last_ms[5], e->ev_call[0], e->ev_call[1]));
         CU(cudaEventElapsedTime(&e->last_ms[2], e->ev_call[1], e->ev_call[2]));
+    }
+    if (bad_id) {
+        e->n = 0;
+        e->n_slots = 0;
+        return fail(P3D_ERR_BAD_ID, "a particle has id >= id_count %u (src/lib.rs:225-228)", id_count);
     }
     return P3D_OK;
 }
@@ -679,7 +730,8 @@ int p3d_download_forces(p3d_engine *e, float *out_xyz, size_t n) {
     CU(cudaSetDevice(e->device));
     int rc;
     if ((rc = e->fout.ensure(n * 3))) return rc;
-    k_unpack_forces<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->frc.p, e->slot_of.p, e->fout.p, (int)n);
+    k_unpack_forces<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->frc.p, e->typed ? e->slot_of.p : nullptr,
+                                                                        e->fout.p, (int)n);
     e->counters[0]++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out_xyz, e->fout.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));

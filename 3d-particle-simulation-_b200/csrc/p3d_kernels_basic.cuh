@@ -27,9 +27,12 @@ __global__ void __launch_bounds__(256) k_fill_ghosts(float4 *__restrict__ pos0, 
 // K3b: AoS (28 B, caller's index order) -> SoA float4 slots (type-sorted).  The block stages its
 // 256 structs through shared memory so that the global reads are fully coalesced 4-byte streams;
 // the per-thread reads from shared memory have stride 7 words (co-prime with 32 banks).
+// slot_of == nullptr: identity layout (slot = caller index); ids are then validated here
+// (err[0] |= 1 for an id >= id_count, the condition src/lib.rs:225-228 would index out of bounds on).
 __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, const uint32_t *__restrict__ slot_of,
                                               float4 *__restrict__ pos, float4 *__restrict__ vel,
-                                              uint32_t *__restrict__ perm, int n) {
+                                              uint32_t *__restrict__ perm, int n, uint32_t id_count,
+                                              int *__restrict__ err) {
     __shared__ float sm[256 * 7];
     const int base = blockIdx.x * 256;
     const int cnt = min(256, n - base);
@@ -39,7 +42,8 @@ __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, con
     const int t = threadIdx.x;
     if (t >= cnt) return;
     const float *p = sm + t * 7;
-    const uint32_t s = slot_of[base + t];
+    const uint32_t s = slot_of ? slot_of[base + t] : (uint32_t)(base + t);
+    if (f2u(p[6]) >= id_count) atomicOr(err, 1);
     pos[s] = make_float4(p[0], p[1], p[2], p[6]);  // w carries the id bits
     vel[s] = make_float4(p[3], p[4], p[5], 0.f);
     perm[s] = (uint32_t)(base + t);
@@ -54,7 +58,7 @@ __global__ void __launch_bounds__(256) k_unpack(const float4 *__restrict__ pos, 
     const int cnt = min(256, n - base);
     const int t = threadIdx.x;
     if (t < cnt) {
-        const uint32_t s = slot_of[base + t];
+        const uint32_t s = slot_of ? slot_of[base + t] : (uint32_t)(base + t);
         const float4 p = pos[s];
         const float4 v = vel[s];
         float *o = sm + t * 7;
@@ -73,7 +77,7 @@ __global__ void __launch_bounds__(256) k_unpack_forces(const float4 *__restrict_
                                                        float *__restrict__ out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 f = frc[slot_of[i]];
+    const float4 f = frc[slot_of ? slot_of[i] : (uint32_t)i];
     out[3 * i] = f.x; out[3 * i + 1] = f.y; out[3 * i + 2] = f.z;
 }
 

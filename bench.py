@@ -236,7 +236,7 @@ def run_engine(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "f32", "data": "synthetic", "force_kernel": "k_force_pair: all N^2 pairs (north_star); the cell list is reported separately",
         "config": config_dict(n, W, {"parallelism": f"block rows sharded over {world} GPU(s); per step all-reduce(forces) + all-gather(positions) over NCCL" if world > 1 else "1 GPU",
                                      "block": args.block}),
         "steps_per_s": 1e3 / ms_per_step,
@@ -330,6 +330,38 @@ def run_engine(args):
                        "d2h_bytes_per_step": n * 28, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                        "api": "per rank: p3d_upload + sharded step + p3d_download on pinned host arrays"}
 
+    # ---------------- "next" row: the cell-list path on the same workload ----------------
+    # Reported as effective steps/s only: it evaluates ~30 candidates per particle instead of N, so it
+    # must never be read against the FP32 roofline.
+    if world == 1 and rank == 0 and not args.no_cells:
+        eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_CELLS)
+        eng.set_option(_abi.OPT_TIMING, 0)
+        eng.upload(parts, prm["id_count"])
+        eng.step(P, TS, 5)
+        eng.sync()
+        c_steps = 50
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        eng.step(P, TS, c_steps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        c_ms = e0.elapsed_time(e1) / c_steps
+        a_in[:] = parts
+        eng.update_into(P, TS, a_in, a_out)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            eng.update_into(P, TS, a_in, a_out)
+            a_in, a_out = a_out, a_in
+        c_e2e = (time.perf_counter() - t0) / 5
+        line["cell_list"] = {
+            "what": "P3D_FORCE_CELLS: GPU uniform grid, the analogue of the reference's spatial hash (src/lib.rs:135-236); "
+                    "same results within the parity tolerance; NOT all-pairs, so no roofline fraction",
+            "ms_per_step": c_ms, "steps_per_s": 1e3 / c_ms,
+            "e2e_ms_per_step": c_e2e * 1e3, "e2e_steps_per_s": 1.0 / c_e2e,
+            "all_pairs_equivalent_interactions_per_s": float(n) * n / (c_ms * 1e-3),
+        }
+        eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_PAIR)
+
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     if world == 1 and rank == 0 and not args.no_cpu:
         r = cpu_reference_sample(prm, parts, args.cpu_seconds)
@@ -360,6 +392,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cells", action="store_true", help="skip the cell-list (SURVEY §8f-1) section")
     args = ap.parse_args()
     if args.world_size is None:
         args.world_size = W_DEFAULT if args.n == N_DEFAULT else round(float(args.n) ** (1.0 / 3.0), 1)
