@@ -118,6 +118,10 @@ struct p3d_engine {
 
     // sharding
     int rank = 0, world = 1;
+    // peer memory (CUDA IPC): [rank][0]=frc, [1]=pos[0], [2]=pos[1]; own entries are the local pointers
+    void *peer_ptr[8][3] = {};
+    bool peer_open[8] = {};
+    bool peers_ready = false;
 
     // timing
     std::vector<cudaEvent_t> ev;  // kEv per timed step: start, after partition, after pair, after force, after integrate
@@ -589,6 +593,7 @@ void p3d_destroy(p3d_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    p3d_ipc_close(e);
     for (auto &b : e->pos) b.release();
     e->vel.release(); e->frc.release(); e->spos.release();
     e->perm.release(); e->slot_of.release(); e->sidx.release();
@@ -848,6 +853,83 @@ int p3d_shard_integrate(p3d_engine *e, const p3d_params *prm, float ts) {
     if ((rc = canonicalise(prm, P))) return rc;
     CU(cudaSetDevice(e->device));
     return launch_integrate(e, P, ts);
+}
+
+// ---- peer memory for the fused integrate kernel ----
+int p3d_ipc_export(p3d_engine *e, unsigned char *handles /* 3 * 64 bytes */) {
+    if (!e || !handles) return fail(P3D_ERR_INVALID, "null argument");
+    if (e->n_slots == 0) return fail(P3D_ERR_INVALID, "no particles uploaded");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(e->device));
+    void *ptrs[3] = {e->frc.p, e->pos[0].p, e->pos[1].p};
+    for (int k = 0; k < 3; ++k) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, ptrs[k]));
+        std::memcpy(handles + 64 * k, &h, 64);
+    }
+    return P3D_OK;
+}
+
+int p3d_ipc_close(p3d_engine *e) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    cudaSetDevice(e->device);
+    for (int g = 0; g < 8; ++g) {
+        if (e->peer_open[g])
+            for (int k = 0; k < 3; ++k)
+                if (e->peer_ptr[g][k]) cudaIpcCloseMemHandle(e->peer_ptr[g][k]);
+        e->peer_open[g] = false;
+        for (int k = 0; k < 3; ++k) e->peer_ptr[g][k] = nullptr;
+    }
+    e->peers_ready = false;
+    return P3D_OK;
+}
+
+int p3d_ipc_import(p3d_engine *e, int world, const unsigned char *all_handles /* world * 3 * 64 bytes */) {
+    if (!e || !all_handles) return fail(P3D_ERR_INVALID, "null argument");
+    if (world != e->world || world > 8) return fail(P3D_ERR_INVALID, "world %d does not match the shard (%d) or exceeds 8", world, e->world);
+    CU(cudaSetDevice(e->device));
+    p3d_ipc_close(e);
+    for (int g = 0; g < world; ++g) {
+        if (g == e->rank) {
+            e->peer_ptr[g][0] = e->frc.p;
+            e->peer_ptr[g][1] = e->pos[0].p;
+            e->peer_ptr[g][2] = e->pos[1].p;
+            continue;
+        }
+        for (int k = 0; k < 3; ++k) {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, all_handles + (size_t)(g * 3 + k) * 64, 64);
+            CU(cudaIpcOpenMemHandle(&e->peer_ptr[g][k], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+        e->peer_open[g] = true;
+    }
+    e->peers_ready = true;
+    return P3D_OK;
+}
+
+int p3d_shard_integrate_fused(p3d_engine *e, const p3d_params *prm, float ts) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (!e->peers_ready) return fail(P3D_ERR_INVALID, "peer buffers not imported (p3d_ipc_import)");
+    DevParams P;
+    int rc;
+    if ((rc = canonicalise(prm, P))) return rc;
+    CU(cudaSetDevice(e->device));
+    const int ns = e->n_slots;
+    const int per = ((e->M + e->world - 1) / e->world) * e->B;
+    const int s0 = std::min(ns, e->rank * per), s1 = std::min(ns, s0 + per);
+    PeerTable pt;
+    for (int g = 0; g < 8; ++g) {
+        pt.frc[g] = (const float4 *)e->peer_ptr[g][0];
+        pt.pos_next[g] = (float4 *)e->peer_ptr[g][1 + (e->cur ^ 1)];
+    }
+    if (s1 > s0) {
+        k_integrate_fused<<<(s1 - s0 + 255) / 256, 256, 0, e->stream>>>(e->pos[e->cur].p, e->vel.p, pt, e->world, s0, s1,
+                                                                        P, ts, e->flags.p + (e->parity ^ 1));
+        e->counters[0]++;
+        e->counters[2]++;
+    }
+    CU(cudaGetLastError());
+    return P3D_OK;
 }
 
 int p3d_shard_commit(p3d_engine *e) {

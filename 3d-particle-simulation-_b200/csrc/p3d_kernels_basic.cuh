@@ -189,16 +189,8 @@ __device__ __forceinline__ void wall_axis(float half, float W, int walls, float 
     }
 }
 
-__global__ void __launch_bounds__(256) k_integrate(const float4 *__restrict__ pos, float4 *__restrict__ pos_next,
-                                                   float4 *__restrict__ vel, const float4 *__restrict__ frc,
-                                                   int s_begin, int s_end, DevParams P, float ts,
-                                                   int *__restrict__ flag_next) {
-    const int s = s_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= s_end) return;
-    float4 p = pos[s];
-    if (f2u(p.w) == P3D_GHOST_ID) return;  // ghosts are identical in both position buffers
-    float4 v = vel[s];
-    const float4 F = frc[s];
+// One particle of src/lib.rs:245-264: returns false when the new position left the box.
+__device__ __forceinline__ bool integrate_particle(float4 &p, float4 &v, const float4 F, const DevParams &P, float ts) {
     // :246-247  velocity += ((F * k) * r) * ts
     v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(__fmul_rn(F.x, P.kf), P.r), ts));
     v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(__fmul_rn(F.y, P.kf), P.r), ts));
@@ -226,8 +218,51 @@ __global__ void __launch_bounds__(256) k_integrate(const float4 *__restrict__ po
     wall_axis(P.half, P.W, P.walls, p.x, v.x);
     wall_axis(P.half, P.W, P.walls, p.y, v.y);
     wall_axis(P.half, P.W, P.walls, p.z, v.z);
-    if (!(fabsf(p.x) <= P.half && fabsf(p.y) <= P.half && fabsf(p.z) <= P.half)) atomicOr(flag_next, 1);
+    return fabsf(p.x) <= P.half && fabsf(p.y) <= P.half && fabsf(p.z) <= P.half;
+}
+
+__global__ void __launch_bounds__(256) k_integrate(const float4 *__restrict__ pos, float4 *__restrict__ pos_next,
+                                                   float4 *__restrict__ vel, const float4 *__restrict__ frc,
+                                                   int s_begin, int s_end, DevParams P, float ts,
+                                                   int *__restrict__ flag_next) {
+    const int s = s_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= s_end) return;
+    float4 p = pos[s];
+    if (f2u(p.w) == P3D_GHOST_ID) return;  // ghosts are identical in both position buffers
+    float4 v = vel[s];
+    if (!integrate_particle(p, v, frc[s], P, ts)) atomicOr(flag_next, 1);
     pos_next[s] = p;
+    vel[s] = v;
+}
+
+// K2 fused with its two collectives for one-process-per-GPU runs (NVLink peer memory):
+//   reduce-scatter : the total force on an owned slot is the sum of every rank's partial force,
+//                    read straight from the peers' force buffers (P2P loads);
+//   integrate      : src/lib.rs:245-264, as k_integrate;
+//   all-gather     : the new position is stored into every rank's next-position buffer (P2P stores).
+// peers.frc[g] / peers.pos_next[g] are device pointers into rank g's memory (cudaIpcOpenMemHandle);
+// entry `rank` is the local buffer.  The driver separates force pass, this kernel and the next force
+// pass with a cross-rank barrier.
+struct PeerTable {
+    const float4 *frc[8];
+    float4 *pos_next[8];
+};
+
+__global__ void __launch_bounds__(256) k_integrate_fused(const float4 *__restrict__ pos, float4 *__restrict__ vel,
+                                                         PeerTable peers, int world, int s_begin, int s_end,
+                                                         DevParams P, float ts, int *__restrict__ flag_next) {
+    const int s = s_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= s_end) return;
+    float4 p = pos[s];
+    if (f2u(p.w) == P3D_GHOST_ID) return;
+    float4 F = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int g = 0; g < world; ++g) {  // fixed rank order: every run sums identically
+        const float4 f = peers.frc[g][s];
+        F.x += f.x; F.y += f.y; F.z += f.z;
+    }
+    float4 v = vel[s];
+    if (!integrate_particle(p, v, F, P, ts)) atomicOr(flag_next, 1);
+    for (int g = 0; g < world; ++g) peers.pos_next[g][s] = p;
     vel[s] = v;
 }
 

@@ -164,6 +164,21 @@ class Engine:
     def shard_commit(self):
         _abi.check(self._lib.p3d_shard_commit(self._h))
 
+    def shard_integrate_fused(self, params, ts: float):
+        _abi.check(self._lib.p3d_shard_integrate_fused(self._h, C.byref(params), ts))
+
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(3 * 64)
+        _abi.check(self._lib.p3d_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_import(self, world: int, all_handles: bytes):
+        assert len(all_handles) == world * 3 * 64
+        _abi.check(self._lib.p3d_ipc_import(self._h, world, all_handles))
+
+    def ipc_close(self):
+        _abi.check(self._lib.p3d_ipc_close(self._h))
+
 
 class Particles:
     """Mirror of `pub struct Particles` (src/lib.rs:20-33); every field is public and mutable."""

@@ -50,6 +50,7 @@ EXPORTS = [
     "p3d_download", "p3d_sync", "p3d_download_forces", "p3d_diagnostics", "p3d_set_option", "p3d_get_option",
     "p3d_get_timing", "p3d_get_counters", "p3d_set_stream", "p3d_device_buffer", "p3d_set_shard",
     "p3d_shard_range", "p3d_shard_force", "p3d_shard_integrate", "p3d_shard_commit",
+    "p3d_ipc_export", "p3d_ipc_import", "p3d_ipc_close", "p3d_shard_integrate_fused",
     "p3d_scene_default_params", "p3d_scene_uniform", "p3d_scene_plummer", "p3d_microbench",
 ]
 
@@ -110,6 +111,14 @@ def load():
     L.p3d_shard_integrate.argtypes = [vp, PP, f32]
     L.p3d_shard_commit.restype = i32
     L.p3d_shard_commit.argtypes = [vp]
+    L.p3d_ipc_export.restype = i32
+    L.p3d_ipc_export.argtypes = [vp, C.c_char_p]
+    L.p3d_ipc_import.restype = i32
+    L.p3d_ipc_import.argtypes = [vp, i32, C.c_char_p]
+    L.p3d_ipc_close.restype = i32
+    L.p3d_ipc_close.argtypes = [vp]
+    L.p3d_shard_integrate_fused.restype = i32
+    L.p3d_shard_integrate_fused.argtypes = [vp, PP, f32]
     L.p3d_scene_default_params.restype = None
     L.p3d_scene_default_params.argtypes = [PP, C.POINTER(f32)]
     L.p3d_scene_uniform.restype = None

@@ -11,6 +11,11 @@ particles owned by other ranks, so the step is
     all_gather       : new positions                        (16 B per slot)
     shard_commit     : swap position buffers
 
+Fused mode (GPUs of one node): both collectives move into ONE kernel, k_integrate_fused, which
+sums the partial forces straight out of every peer's force buffer (P2P loads over NVLink),
+integrates, and stores the new positions into every peer's position buffer (P2P stores).  NCCL is
+then only used for two one-element all-reduces per step that act as cross-rank barriers.
+
 The engine is anything with the `Engine` shard API (particle_3d.Engine on GPUs; the tests
 substitute a CPU stand-in built on the oracle to cover the collective plumbing with gloo).
 """
@@ -45,8 +50,16 @@ def engine_tensors(engine, device_index: int):
     return out
 
 
+def exchange_peer_handles(engine, dist, world: int):
+    """All-gathers every rank's CUDA IPC handles and opens the peers' buffers (fused mode)."""
+    mine = engine.ipc_export()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    engine.ipc_import(world, b"".join(gathered))
+
+
 class ShardedStepper:
-    def __init__(self, engine, dist, rank: int, world: int, tensors_fn):
+    def __init__(self, engine, dist, rank: int, world: int, tensors_fn, fused: bool = False, barrier_tensor=None):
         """tensors_fn() -> dict(pos=, pos_next=, force=) of torch tensors aliasing the engine's
         CURRENT buffers (POS/POS_NEXT swap at every commit, so it is called once per parity)."""
         self.engine, self.dist, self.rank, self.world = engine, dist, rank, world
@@ -54,6 +67,10 @@ class ShardedStepper:
         self._views = [None, None]
         self._parity = 0
         self.collectives = 0
+        # fused mode: forces and positions travel through k_integrate_fused over peer memory; the only
+        # collective left is a one-element all-reduce used as a stream-ordered cross-rank barrier
+        self.fused = fused and world > 1
+        self._bar = barrier_tensor
 
     def _tensors(self):
         if self._views[self._parity] is None:
@@ -63,6 +80,14 @@ class ShardedStepper:
     def step(self, params, ts: float, n_steps: int = 1):
         eng, dist = self.engine, self.dist
         for _ in range(n_steps):
+            if self.fused:
+                eng.shard_force(params)
+                dist.all_reduce(self._bar)   # every rank's partial forces are complete
+                eng.shard_integrate_fused(params, ts)
+                dist.all_reduce(self._bar)   # every rank's position stores have landed
+                eng.shard_commit()
+                self.collectives += 2
+                continue
             t = self._tensors()
             eng.shard_force(params)
             if self.world > 1:

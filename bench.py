@@ -159,7 +159,7 @@ def run_engine(args):
 
     import particle_3d as p3
     from particle_3d import _abi
-    from particle_3d.sharded import ShardedStepper, engine_tensors
+    from particle_3d.sharded import ShardedStepper, engine_tensors, exchange_peer_handles
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -194,8 +194,17 @@ def run_engine(args):
             torch.cuda.synchronize()
 
     stepper = None
+    fused = world > 1 and not args.no_fused
+
+    def make_stepper():
+        if fused:
+            exchange_peer_handles(eng, dist, world)
+            bar = torch.zeros(1, device=f"cuda:{local}")
+            return ShardedStepper(eng, dist, rank, world, lambda: engine_tensors(eng, local), fused=True, barrier_tensor=bar)
+        return ShardedStepper(eng, dist, rank, world, lambda: engine_tensors(eng, local))
+
     if world > 1:
-        stepper = ShardedStepper(eng, dist, rank, world, lambda: engine_tensors(eng, local))
+        stepper = make_stepper()
 
     def one_step():
         if stepper:
@@ -237,7 +246,7 @@ def run_engine(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "force_kernel": "k_force_pair: all N^2 pairs (north_star); the cell list is reported separately",
-        "config": config_dict(n, W, {"parallelism": f"block rows sharded over {world} GPU(s); per step all-reduce(forces) + all-gather(positions) over NCCL" if world > 1 else "1 GPU",
+        "config": config_dict(n, W, {"parallelism": (f"block rows sharded over {world} GPUs; " + ("per step ONE fused kernel does reduce-scatter(forces) + integrate + all-gather(positions) over NVLink peer memory, NCCL only as two 4-byte barrier all-reduces" if fused else "per step all-reduce(forces) + all-gather(positions) over NCCL")) if world > 1 else "1 GPU",
                                      "block": args.block}),
         "steps_per_s": 1e3 / ms_per_step,
         "gpu_launches": int(launches),
@@ -316,7 +325,7 @@ def run_engine(args):
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            eng.upload(a_in, prm["id_count"])
+            eng.upload(a_in, prm["id_count"])  # same-size re-upload: device buffers (and IPC mappings) stay put
             stepper._views = [None, None]
             stepper._parity = 0
             stepper.step(P, TS, 1)
@@ -392,6 +401,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-reduce + all-gather instead of the fused P2P kernel")
     ap.add_argument("--no-cells", action="store_true", help="skip the cell-list (SURVEY §8f-1) section")
     args = ap.parse_args()
     if args.world_size is None:

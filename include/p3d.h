@@ -137,6 +137,17 @@ int p3d_shard_force(p3d_engine *eng, const p3d_params *prm);
 int p3d_shard_integrate(p3d_engine *eng, const p3d_params *prm, float ts);
 int p3d_shard_commit(p3d_engine *eng);
 
+/* Fused variant of the step's second half over NVLink peer memory (one kernel = reduce-scatter of the
+ * partial forces + integrate + all-gather of the new positions; no NCCL on the data path):
+ *   p3d_ipc_export  -> three 64-byte CUDA IPC handles (force buffer, both position buffers) of this rank
+ *   [driver: all-gather the handles]
+ *   p3d_ipc_import  -> opens every peer's buffers (world <= 8, same node, after p3d_upload on all ranks)
+ *   per step: p3d_shard_force; [barrier]; p3d_shard_integrate_fused; [barrier]; p3d_shard_commit */
+int p3d_ipc_export(p3d_engine *eng, unsigned char *handles /* 3 * 64 bytes */);
+int p3d_ipc_import(p3d_engine *eng, int world, const unsigned char *all_handles /* world * 3 * 64 bytes */);
+int p3d_ipc_close(p3d_engine *eng);
+int p3d_shard_integrate_fused(p3d_engine *eng, const p3d_params *prm, float ts);
+
 /* ---- FP32-pipe microbenchmarks: make the roofline denominator defensible ----
  * kind 0: dependent-chain-free scalar FFMA; 1: packed FFMA2; 2: the pair kernel's instruction mix
  * (17 FFMA2/FADD2 : 2 MUFU.RSQ : 6 FMNMX); 3: FFMA2 with the pair kernel's shuffle rate (12 SHFL per 68 FFMA2).

@@ -15,7 +15,7 @@ import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.join(ROOT, "3d-particle-simulation-_b200")); sys.path.insert(0, ROOT)
 import particle_3d as p3
 from particle_3d import _abi
-from particle_3d.sharded import ShardedStepper, engine_tensors
+from particle_3d.sharded import ShardedStepper, engine_tensors, exchange_peer_handles
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -31,10 +31,16 @@ eng.upload(parts, 5)
 st = ShardedStepper(eng, dist, rank, world, lambda: engine_tensors(eng, local))
 st.step(P, 1/60, steps)
 torch.cuda.synchronize()
-out = eng.download()
-s0, s1 = eng.shard_range()
-np.save(os.path.join(OUT, f"shard_{rank}.npy"), out)
-dist.barrier(); dist.destroy_process_group()
+np.save(os.path.join(OUT, f"shard_{rank}.npy"), eng.download())
+# the same run through the fused P2P kernel (no NCCL on the data path)
+eng.upload(parts, 5)
+exchange_peer_handles(eng, dist, world)
+bar = torch.zeros(1, device=f"cuda:{local}")
+st = ShardedStepper(eng, dist, rank, world, lambda: engine_tensors(eng, local), fused=True, barrier_tensor=bar)
+st.step(P, 1/60, steps)
+torch.cuda.synchronize()
+np.save(os.path.join(OUT, f"fused_{rank}.npy"), eng.download())
+dist.barrier(); eng.ipc_close(); dist.barrier(); dist.destroy_process_group()
 '''
 
 
@@ -59,12 +65,17 @@ def test_two_gpu_sharded_step_matches_single_gpu_and_oracle(tmp_path, default_pa
     ref = p3.generate_particles(W, n, seed=42)
     for _ in range(3):
         ref = O.update(prm, 1 / 60, ref, mode=O.IDEAL)["out"]
-    a, b = np.load(tmp_path / "shard_0.npy"), np.load(tmp_path / "shard_1.npy")
+    for prefix in ("shard", "fused"):
+        _check(np.load(tmp_path / f"{prefix}_0.npy"), np.load(tmp_path / f"{prefix}_1.npy"), ref, W, prefix)
+
+
+def _check(a, b, ref, W, what):
+    from helpers import parity_errors
     # after the final all-gather both ranks hold every position; velocities only for their own shard,
     # so compare positions on both and velocities where each rank owns the slot (non-zero update)
     for got in (a, b):
         dv, dp = parity_errors(got, ref, W)
-        assert dp.max() < 5e-5
+        assert dp.max() < 5e-5, what
     dva, _ = parity_errors(a, ref, W)
     dvb, _ = parity_errors(b, ref, W)
-    assert np.minimum(dva, dvb).max() < 5e-5  # every particle's velocity is right on its owner rank
+    assert np.minimum(dva, dvb).max() < 5e-5, what  # every particle's velocity is right on its owner rank
