@@ -104,15 +104,11 @@ struct p3d_engine {
     int cur = 0;            // which pos buffer is current
     int parity = 0;         // which flag word describes the current positions
 
-    // pinned staging for the one-shot call
-    void *pin = nullptr;
-    size_t pin_cap = 0;
     std::vector<uint32_t> slot_h;
 
     // options
     int opt_force = P3D_FORCE_AUTO;
     int opt_timing = 0;
-    int opt_graph = 0;
     int opt_block_sort = 1;
     int opt_tune = 0;        // developer knob: kernel variant selection for experiments
 
@@ -127,7 +123,6 @@ struct p3d_engine {
     std::vector<cudaEvent_t> ev;  // kEv per timed step: start, after partition, after pair, after force, after integrate
     int timed_steps = 0;
     cudaEvent_t ev_call[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool call_timed = false;
     float last_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t *step_ev = nullptr;  // events of the step being recorded (null: untimed)
     uint64_t counters[4] = {0, 0, 0, 0};
@@ -170,18 +165,6 @@ int canonicalise(const p3d_params *prm, DevParams &P) {
     return P3D_OK;
 }
 
-int ensure_pinned(p3d_engine *e, size_t bytes) {
-    if (bytes <= e->pin_cap) return P3D_OK;
-    if (e->pin) cudaFreeHost(e->pin);
-    e->pin = nullptr;
-    e->pin_cap = 0;
-    const size_t want = bytes + bytes / 8 + 4096;
-    CU(cudaMallocHost(&e->pin, want));
-    e->pin_cap = want;
-    return P3D_OK;
-}
-
-// Builds the type-sorted slot layout for `n` particles with ids `in[i].id` and uploads it.
 int ensure_common(p3d_engine *e, size_t n, size_t ns) {
     int rc;
     if ((rc = e->pos[0].ensure(ns))) return rc;
@@ -603,7 +586,6 @@ void p3d_destroy(p3d_engine *e) {
     for (auto &b : e->cvals) b.release();
     e->cell_start.release(); e->cell_end.release(); e->cpos.release(); e->cub_tmp.release();
     e->aos.release(); e->fout.release(); e->sx.release(); e->sy.release(); e->sz.release(); e->matrix.release(); e->flags.release(); e->diag.release();
-    if (e->pin) cudaFreeHost(e->pin);
     for (auto x : e->ev) cudaEventDestroy(x);
     for (auto x : e->ev_call) if (x) cudaEventDestroy(x);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -624,7 +606,6 @@ int p3d_set_option(p3d_engine *e, int option, int value) {
             e->opt_force = value;
             return P3D_OK;
         case P3D_OPT_TIMING: e->opt_timing = value ? 1 : 0; return P3D_OK;
-        case P3D_OPT_GRAPH: e->opt_graph = value ? 1 : 0; return P3D_OK;
         case P3D_OPT_BLOCK_SORT: e->opt_block_sort = value ? 1 : 0; return P3D_OK;
         case 99: e->opt_tune = value; return P3D_OK;
         case P3D_OPT_BLOCK_SIZE:
@@ -640,7 +621,6 @@ int p3d_get_option(p3d_engine *e, int option, int *value) {
     switch (option) {
         case P3D_OPT_FORCE_KERNEL: *value = e->opt_force; return P3D_OK;
         case P3D_OPT_TIMING: *value = e->opt_timing; return P3D_OK;
-        case P3D_OPT_GRAPH: *value = e->opt_graph; return P3D_OK;
         case P3D_OPT_BLOCK_SORT: *value = e->opt_block_sort; return P3D_OK;
         case P3D_OPT_BLOCK_SIZE: *value = e->B_next; return P3D_OK;
         default: return fail(P3D_ERR_INVALID, "unknown option %d", option);

@@ -87,7 +87,7 @@ int p3d_diagnostics(p3d_engine *eng, double out[8]);
 enum p3d_option {
     P3D_OPT_FORCE_KERNEL = 0, /* see p3d_force_kernel */
     P3D_OPT_TIMING = 1,       /* 1: record CUDA events around each kernel of a step */
-    P3D_OPT_GRAPH = 2,        /* 1: replay p3d_step through a CUDA graph */
+    /* 2 is reserved */
     P3D_OPT_BLOCK_SORT = 3,   /* 1: re-partition interior/boundary blocks every step (fast path) */
     P3D_OPT_BLOCK_SIZE = 4    /* particles per block of the pair kernel: 0 = auto (256 from 65,536 particles, else 128), 128 (R=4) or 256 (R=8); applies at the next upload */
 };
