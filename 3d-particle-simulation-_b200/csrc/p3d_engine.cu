@@ -110,6 +110,7 @@ struct p3d_engine {
     int opt_force = P3D_FORCE_AUTO;
     int opt_timing = 0;
     int opt_block_sort = 1;
+    int opt_faithful = 0;    // K5: add the reference's bucket double-visit contributions
     int opt_tune = 0;        // developer knob: kernel variant selection for experiments
 
     // sharding
@@ -306,6 +307,79 @@ int resolve_force_kernel(const p3d_engine *e) { return resolve_force_kernel_for(
 
 size_t ref_smem(int tile, int T) { return (size_t)tile * sizeof(float4) + (size_t)T * T * sizeof(float); }
 
+// Sorts the slots by grid cell (cells of edge W/nc >= reach; at most ~8 cells per particle so sparse
+// scenes stay cheap).  g.nc < 3 on return: the box is narrower than three cells, no cell list was built.
+int build_cells(p3d_engine *e, const DevParams &P, const float4 *pos, int *flag_to_clear, CellGrid &g) {
+    cudaStream_t st = e->stream;
+    const int ns = e->n_slots;
+    const float reach = P.reach * 1.001f + 1.0e-4f;
+    long long nc = (long long)std::floor((double)P.W / (double)reach);
+    const long long cap = (long long)std::cbrt(8.0 * (double)std::max<size_t>(e->n, 64)) + 1;
+    nc = std::min<long long>(std::min<long long>(nc, cap), 1024);
+    g.nc = (int)std::max<long long>(nc, 0);
+    g.inv_cs = (float)((double)nc / (double)P.W);
+    g.half = P.half;
+    if (nc < 3) {
+        CU(cudaMemsetAsync(flag_to_clear, 0, sizeof(int), st));
+        return P3D_OK;
+    }
+    const size_t ncell = (size_t)(nc * nc * nc);
+    int rc;
+    for (int k = 0; k < 2; ++k) {
+        if ((rc = e->ckeys[k].ensure((size_t)ns))) return rc;
+        if ((rc = e->cvals[k].ensure((size_t)ns))) return rc;
+    }
+    if ((rc = e->cpos.ensure((size_t)ns))) return rc;
+    if ((rc = e->cell_start.ensure(ncell + 1))) return rc;
+    if ((rc = e->cell_end.ensure(ncell + 1))) return rc;
+    int end_bit = 1;
+    while ((1ull << end_bit) <= ncell) ++end_bit;
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, e->ckeys[0].p, e->ckeys[1].p, e->cvals[0].p, e->cvals[1].p,
+                                       ns, 0, end_bit, st));
+    if ((rc = e->cub_tmp.ensure(tmp_bytes))) return rc;
+    CU(cudaMemsetAsync(e->cell_start.p, 0xFF, (ncell + 1) * sizeof(uint32_t), st));
+    k_cell_keys<<<(ns + 255) / 256, 256, 0, st>>>(pos, ns, g, e->ckeys[0].p, e->cvals[0].p, flag_to_clear);
+    CU(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp_bytes, e->ckeys[0].p, e->ckeys[1].p, e->cvals[0].p,
+                                       e->cvals[1].p, ns, 0, end_bit, st));
+    k_cell_gather<<<(ns + 255) / 256, 256, 0, st>>>(pos, ns, e->ckeys[1].p, e->cvals[1].p, e->cpos.p,
+                                                   e->cell_start.p, e->cell_end.p);
+    e->counters[0] += 3;
+    CU(cudaGetLastError());
+    return P3D_OK;
+}
+
+// K5: adds the reference's double-visit contributions to the ideal forces already in frc.
+int launch_quirk(p3d_engine *e, const DevParams &P, const CellGrid &g, const int *flag_cur) {
+    const int ns = e->n_slots;
+    const int per = (ns + e->world - 1) / e->world;
+    const int i0 = std::min(ns, e->rank * per), i1 = std::min(ns, i0 + per);
+    if (i1 > i0 && e->n > 0) {
+        const size_t sm = (size_t)P.T * P.T * sizeof(float);
+        if (P.rcut)
+            k_quirk_correction<true><<<(i1 - i0 + 127) / 128, 128, sm, e->stream>>>(
+                e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_start.p, e->cell_end.p, i0, i1, g, e->frc.p, P,
+                e->matrix.p, flag_cur, (unsigned long long)e->n);
+        else
+            k_quirk_correction<false><<<(i1 - i0 + 127) / 128, 128, sm, e->stream>>>(
+                e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_start.p, e->cell_end.p, i0, i1, g, e->frc.p, P,
+                e->matrix.p, flag_cur, (unsigned long long)e->n);
+        e->counters[0]++;
+    }
+    CU(cudaGetLastError());
+    return P3D_OK;
+}
+
+// K5 after a force kernel that did not build the cell list itself.
+int launch_quirk_standalone(p3d_engine *e, const DevParams &P, const float4 *pos, const int *flag_cur) {
+    CellGrid g;
+    int rc;
+    int *scratch_flag = e->flags.p + 3;  // build_cells clears a flag word; the step flags are already set
+    if ((rc = build_cells(e, P, pos, scratch_flag, g))) return rc;
+    if (g.nc < 3) return P3D_OK;  // box narrower than three cells: the correction is not available
+    return launch_quirk(e, P, g, flag_cur);
+}
+
 // Force pass for the rows / slots of this shard.  Leaves total_force (src/lib.rs:177-243) in frc.
 int launch_force(p3d_engine *e, const DevParams &P) {
     cudaStream_t st = e->stream;
@@ -331,40 +405,13 @@ int launch_force(p3d_engine *e, const DevParams &P) {
             e->counters[1]++;
         }
         CU(cudaGetLastError());
-        return P3D_OK;
+        return e->opt_faithful ? launch_quirk_standalone(e, P, pos, flag_cur) : P3D_OK;
     }
     if (kind == P3D_FORCE_CELLS) {
-        // cells of edge W/nc >= reach; at most ~8 cells per particle so sparse scenes stay cheap
-        const float reach = P.reach * 1.001f + 1.0e-4f;
-        long long nc = (long long)std::floor((double)P.W / (double)reach);
-        const long long cap = (long long)std::cbrt(8.0 * (double)std::max<size_t>(e->n, 64)) + 1;
-        nc = std::min<long long>(std::min<long long>(nc, cap), 1024);
-        if (nc >= 3) {
-            const size_t ncell = (size_t)(nc * nc * nc);
-            int rc;
-            for (int k = 0; k < 2; ++k) {
-                if ((rc = e->ckeys[k].ensure((size_t)ns))) return rc;
-                if ((rc = e->cvals[k].ensure((size_t)ns))) return rc;
-            }
-            if ((rc = e->cpos.ensure((size_t)ns))) return rc;
-            if ((rc = e->cell_start.ensure(ncell + 1))) return rc;
-            if ((rc = e->cell_end.ensure(ncell + 1))) return rc;
-            int end_bit = 1;
-            while ((1ull << end_bit) <= ncell) ++end_bit;
-            size_t tmp_bytes = 0;
-            CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, e->ckeys[0].p, e->ckeys[1].p, e->cvals[0].p,
-                                               e->cvals[1].p, ns, 0, end_bit, st));
-            if ((rc = e->cub_tmp.ensure(tmp_bytes))) return rc;
-            CellGrid g;
-            g.nc = (int)nc;
-            g.inv_cs = (float)((double)nc / (double)P.W);
-            g.half = P.half;
-            CU(cudaMemsetAsync(e->cell_start.p, 0xFF, (ncell + 1) * sizeof(uint32_t), st));
-            k_cell_keys<<<(ns + 255) / 256, 256, 0, st>>>(pos, ns, g, e->ckeys[0].p, e->cvals[0].p, flag_next);
-            CU(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp_bytes, e->ckeys[0].p, e->ckeys[1].p, e->cvals[0].p,
-                                               e->cvals[1].p, ns, 0, end_bit, st));
-            k_cell_gather<<<(ns + 255) / 256, 256, 0, st>>>(pos, ns, e->ckeys[1].p, e->cvals[1].p, e->cpos.p,
-                                                           e->cell_start.p, e->cell_end.p);
+        CellGrid g;
+        int rc;
+        if ((rc = build_cells(e, P, pos, flag_next, g))) return rc;
+        if (g.nc >= 3) {
             if (e->step_ev) CU(cudaEventRecord(e->step_ev[1], st));
             if (e->world > 1) CU(cudaMemsetAsync(e->frc.p, 0, (size_t)ns * sizeof(float4), st));
             const int per = (ns + e->world - 1) / e->world;
@@ -379,9 +426,9 @@ int launch_force(p3d_engine *e, const DevParams &P) {
                     k_force_cells<false><<<(i1 - i0 + 127) / 128, 128, sm, st>>>(
                         e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_start.p, e->cell_end.p, ns, i0, i1, g,
                         e->frc.p, P, e->matrix.p, flag_cur);
+                e->counters[0]++;
+                e->counters[1]++;
             }
-            e->counters[0] += 4;
-            e->counters[1] += 1;
             if (e->step_ev) CU(cudaEventRecord(e->step_ev[2], st));
             // out-of-box inputs (flag set): the reference-order kernel takes the whole step instead
             const int perb = ((e->M + e->world - 1) / e->world) * e->B;
@@ -392,6 +439,7 @@ int launch_force(p3d_engine *e, const DevParams &P) {
                 e->counters[0]++;
             }
             CU(cudaGetLastError());
+            if (e->opt_faithful) return launch_quirk(e, P, g, flag_cur);
             return P3D_OK;
         }
         // box narrower than three cells: the all-pairs path below handles it
@@ -465,7 +513,7 @@ int launch_force(p3d_engine *e, const DevParams &P) {
         }
     }
     CU(cudaGetLastError());
-    return P3D_OK;
+    return e->opt_faithful ? launch_quirk_standalone(e, P, pos, flag_cur) : P3D_OK;
 }
 
 int launch_integrate(p3d_engine *e, const DevParams &P, float ts) {
@@ -607,6 +655,7 @@ int p3d_set_option(p3d_engine *e, int option, int value) {
             return P3D_OK;
         case P3D_OPT_TIMING: e->opt_timing = value ? 1 : 0; return P3D_OK;
         case P3D_OPT_BLOCK_SORT: e->opt_block_sort = value ? 1 : 0; return P3D_OK;
+        case P3D_OPT_FAITHFUL: e->opt_faithful = value ? 1 : 0; return P3D_OK;
         case 99: e->opt_tune = value; return P3D_OK;
         case P3D_OPT_BLOCK_SIZE:
             if (value != 0 && value != 128 && value != 256) return fail(P3D_ERR_INVALID, "block size must be 0 (auto), 128 or 256");
@@ -623,6 +672,7 @@ int p3d_get_option(p3d_engine *e, int option, int *value) {
         case P3D_OPT_TIMING: *value = e->opt_timing; return P3D_OK;
         case P3D_OPT_BLOCK_SORT: *value = e->opt_block_sort; return P3D_OK;
         case P3D_OPT_BLOCK_SIZE: *value = e->B_next; return P3D_OK;
+        case P3D_OPT_FAITHFUL: *value = e->opt_faithful; return P3D_OK;
         default: return fail(P3D_ERR_INVALID, "unknown option %d", option);
     }
 }

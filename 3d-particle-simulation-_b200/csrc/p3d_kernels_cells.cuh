@@ -131,3 +131,124 @@ __global__ void __launch_bounds__(128) k_force_cells(const float4 *__restrict__ 
     }
     frc[vals_sorted[k]] = make_float4(ax, ay, az, 0.f);
 }
+
+// ---------------------------------------------------------------------------------------------
+// K5 — optional "faithful" correction: reproduces the reference's bucket double-visit quirk
+// (SURVEY.md Appendix B.1).  The reference hashes the 27 cells around cell_coord(position + offset)
+// into N buckets (src/lib.rs:195-202) and scans each hit bucket's whole list; a neighbour q is
+// therefore visited once for every one of the 27 cells whose bucket equals the bucket of q's own
+// cell — usually once, sometimes twice when two cells collide modulo N.  The ideal force counts
+// every in-range (particle, image) pair once, so the reference's result is
+//     ideal + sum over in-range pairs of (multiplicity - 1) * contribution.
+// This kernel adds that sum.  Restated from the definitions: SipHash-1-3 with zero keys over three
+// little-endian i64 words (Rust DefaultHasher, src/lib.rs:46-52), `(v / r) as isize` (src/lib.rs:37-43).
+__device__ __forceinline__ uint64_t rotl64_dev(uint64_t x, int b) { return (x << b) | (x >> (64 - b)); }
+
+#define P3D_SIPROUND(v0, v1, v2, v3)                                                    \
+    do {                                                                                \
+        v0 += v1; v1 = rotl64_dev(v1, 13); v1 ^= v0; v0 = rotl64_dev(v0, 32);           \
+        v2 += v3; v3 = rotl64_dev(v3, 16); v3 ^= v2;                                    \
+        v0 += v3; v3 = rotl64_dev(v3, 21); v3 ^= v0;                                    \
+        v2 += v1; v1 = rotl64_dev(v1, 17); v1 ^= v2; v2 = rotl64_dev(v2, 32);           \
+    } while (0)
+
+__device__ __forceinline__ uint64_t hash_cell_dev(long long x, long long y, long long z) {
+    uint64_t v0 = 0x736f6d6570736575ULL, v1 = 0x646f72616e646f6dULL;
+    uint64_t v2 = 0x6c7967656e657261ULL, v3 = 0x7465646279746573ULL;
+    uint64_t m;
+    m = (uint64_t)x; v3 ^= m; P3D_SIPROUND(v0, v1, v2, v3); v0 ^= m;
+    m = (uint64_t)y; v3 ^= m; P3D_SIPROUND(v0, v1, v2, v3); v0 ^= m;
+    m = (uint64_t)z; v3 ^= m; P3D_SIPROUND(v0, v1, v2, v3); v0 ^= m;
+    m = (uint64_t)24 << 56; v3 ^= m; P3D_SIPROUND(v0, v1, v2, v3); v0 ^= m;  // length byte of the 24-byte message
+    v2 ^= 0xff;
+    P3D_SIPROUND(v0, v1, v2, v3);
+    P3D_SIPROUND(v0, v1, v2, v3);
+    P3D_SIPROUND(v0, v1, v2, v3);
+    return v0 ^ v1 ^ v2 ^ v3;
+}
+
+// Rust `(v / r) as isize`: IEEE divide, truncate toward zero, saturate, NaN -> 0 (cvt.rzi.s64.f32 does all three).
+__device__ __forceinline__ long long ref_cell_axis(float v, float r) { return __float2ll_rz(__fdiv_rn(v, r)); }
+
+template <bool RCUT>
+__global__ void __launch_bounds__(128) k_quirk_correction(const float4 *__restrict__ cpos,
+                                                          const uint32_t *__restrict__ keys_sorted,
+                                                          const uint32_t *__restrict__ vals_sorted,
+                                                          const uint32_t *__restrict__ cell_start,
+                                                          const uint32_t *__restrict__ cell_end, int i_begin,
+                                                          int i_end, CellGrid g, float4 *__restrict__ frc,
+                                                          DevParams P, const float *__restrict__ matrix,
+                                                          const int *__restrict__ flags, unsigned long long n_hash) {
+    if (flags[0] != 0) return;  // out-of-box input: not supported by the correction (documented)
+    extern __shared__ float smat_dyn[];
+    for (int k = threadIdx.x; k < P.T * P.T; k += blockDim.x) smat_dyn[k] = matrix[k];
+    __syncthreads();
+    const int k = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= i_end) return;
+    const uint32_t key = keys_sorted[k];
+    const int nc = g.nc;
+    if (key >= (uint32_t)(nc * nc * nc)) return;
+    const float4 pi = cpos[k];
+    const int cx = (int)(key % (uint32_t)nc), cy = (int)((key / (uint32_t)nc) % (uint32_t)nc),
+              cz = (int)(key / (uint32_t)(nc * nc));
+    const float *arow = smat_dyn + f2u(pi.w) * (uint32_t)P.T;
+    const float c2 = P.c2, ncm = -P.c2 * P.m, nc2 = -P.c2, im = P.inv_m, r2 = P.r2;
+    const float pxm = __fadd_rn(pi.x, -P.W), pxp = __fadd_rn(pi.x, P.W);
+    const float pym = __fadd_rn(pi.y, -P.W), pyp = __fadd_rn(pi.y, P.W);
+    const float pzm = __fadd_rn(pi.z, -P.W), pzp = __fadd_rn(pi.z, P.W);
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    bool any = false;
+#pragma unroll 1
+    for (int dz = -1; dz <= 1; ++dz) {
+        int nz = cz + dz;
+        float pz = pi.z;
+        if (nz < 0) { nz += nc; pz = pzp; } else if (nz >= nc) { nz -= nc; pz = pzm; }
+#pragma unroll 1
+        for (int dy = -1; dy <= 1; ++dy) {
+            int ny = cy + dy;
+            float py = pi.y;
+            if (ny < 0) { ny += nc; py = pyp; } else if (ny >= nc) { ny -= nc; py = pym; }
+#pragma unroll 1
+            for (int dx = -1; dx <= 1; ++dx) {
+                int nx = cx + dx;
+                float px = pi.x;
+                if (nx < 0) { nx += nc; px = pxp; } else if (nx >= nc) { nx -= nc; px = pxm; }
+                const uint32_t c = (uint32_t)((nz * nc + ny) * nc + nx);
+                const uint32_t s0 = cell_start[c];
+                if (s0 == 0xFFFFFFFFu) continue;
+                const uint32_t s1 = cell_end[c];
+                for (uint32_t j = s0; j < s1; ++j) {
+                    const float4 q = cpos[j];
+                    const float rx = __fsub_rn(q.x, px), ry = __fsub_rn(q.y, py), rz = __fsub_rn(q.z, pz);
+                    // the reference's own cutoff test, in its arithmetic (src/lib.rs:213-220)
+                    const float d2e = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
+                    if (!(d2e > 0.0f && d2e < r2)) continue;
+                    const float inv = rsqrt_approx(d2e);
+                    const float p1 = fmaf(inv, ncm, c2), p2 = fmaf(inv, c2, nc2);
+                    const float ti = fmaxf(fminf(p1, p2), 0.0f);
+                    const float rs = fminf(im - inv, 0.0f);
+                    const float s = fmaf(arow[f2u(q.w)], ti, rs);
+                    if (s == 0.0f) continue;
+                    // multiplicity: how many of the 27 cells around cell_coord(position + offset) share q's bucket
+                    const uint64_t bq = hash_cell_dev(ref_cell_axis(q.x, P.r), ref_cell_axis(q.y, P.r),
+                                                      ref_cell_axis(q.z, P.r)) % n_hash;
+                    const long long c0x = ref_cell_axis(px, P.r), c0y = ref_cell_axis(py, P.r),
+                                    c0z = ref_cell_axis(pz, P.r);
+                    int mult = 0;
+                    for (int ex = -1; ex <= 1; ++ex)
+                        for (int ey = -1; ey <= 1; ++ey)
+                            for (int ez = -1; ez <= 1; ++ez)
+                                mult += (hash_cell_dev(c0x + ex, c0y + ey, c0z + ez) % n_hash) == bq;
+                    if (mult != 1) {
+                        const float w = (float)(mult - 1) * s;
+                        ax = fmaf(rx, w, ax);
+                        ay = fmaf(ry, w, ay);
+                        az = fmaf(rz, w, az);
+                        any = true;
+                    }
+                }
+            }
+        }
+    }
+    if (any) atomicAdd(frc + vals_sorted[k], make_float4(ax, ay, az, 0.0f));
+}

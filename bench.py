@@ -102,10 +102,22 @@ def config_dict(n, W, extra=None):
 
 
 # ------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """All host cores this process may use.  torch.distributed.run exports OMP_NUM_THREADS=1 for N>1,
+    which must not throttle the CPU arm: the thread count is passed to the oracle explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_sample(prm, parts, target_s: float, nthreads: int = 0):
     """Times the CPU restatement of src/lib.rs (oracle, 'port') on a bounded sample of one step:
     the counting sort over all N plus the per-particle pass for the first S particles."""
     from oracle import oracle as O
+
+    if nthreads <= 0:
+        nthreads = host_threads()
 
     n = len(parts)
     probe = min(n, 4096)
@@ -115,7 +127,7 @@ def cpu_reference_sample(prm, parts, target_s: float, nthreads: int = 0):
     _, st = O.update_sample(prm, TS, parts, 0, sample, mode=O.FAITHFUL, nthreads=nthreads)
     step_s = st["t_build_s"] + st["t_force_s"] * (n / sample)
     return {"step_s": step_s, "sample": sample, "build_s": st["t_build_s"], "force_sample_s": st["t_force_s"],
-            "cores": O.num_threads() if nthreads <= 0 else nthreads,
+            "cores": nthreads,
             "candidates_per_particle": st["candidates"] / sample}
 
 

@@ -89,6 +89,10 @@ enum p3d_option {
     P3D_OPT_TIMING = 1,       /* 1: record CUDA events around each kernel of a step */
     /* 2 is reserved */
     P3D_OPT_BLOCK_SORT = 3,   /* 1: re-partition interior/boundary blocks every step (fast path) */
+    P3D_OPT_FAITHFUL = 5,     /* 1: reproduce the reference's bucket double-visit quirk: after the
+                                 ideal force pass a correction kernel adds (multiplicity - 1) x contribution for every
+                                 in-range pair whose bucket is hit by more than one of the 27 hashed cells
+                                 (src/lib.rs:195-206).  Needs in-box positions and a box of at least three cells. */
     P3D_OPT_BLOCK_SIZE = 4    /* particles per block of the pair kernel: 0 = auto (256 from 65,536 particles, else 128), 128 (R=4) or 256 (R=8); applies at the next upload */
 };
 enum p3d_force_kernel {

@@ -348,3 +348,28 @@ def test_shard_partial_forces_sum_to_the_full_force(default_params, kernel, worl
     # the integrate ranges tile the slot array without gaps or overlap
     assert ranges[0][0] == 0 and all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
     assert len({b - a for a, b in ranges}) == 1
+
+
+# ---------------------------------------------------------------- K5: the reference's bucket double-visit quirk
+@pytest.mark.parametrize("kernel", KERNELS, ids=IDS)
+def test_faithful_mode_reproduces_the_reference_quirk(default_params, kernel):
+    """With P3D_OPT_FAITHFUL the GPU matches the FAITHFUL oracle for every particle, including the
+    ones whose neighbours the reference double-counts."""
+    g = np.load(os.path.join(GOLD, "default_scene_n1000_seed42.npz"))
+    e = p3.Engine(0)
+    e.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+    e.set_option(_abi.OPT_FAITHFUL, 1)
+    out = e.update(p3.Engine.make_params(**default_params), TS, g["start"])
+    assert int(g["affected1"].sum()) >= 10
+    assert_parity(out, g["faithful_step1"], 10.0, what="faithful, all particles")
+    dv_ideal, _ = parity_errors(out, g["ideal_step1"], 10.0)
+    assert (dv_ideal > 1e-5).sum() >= 10  # and it really differs from the ideal physics there
+    # a second scene with different N (the bucket count is N): 16,384 particles
+    W = 25.4
+    prm = dict(default_params, world_size=W)
+    start = p3.generate_particles(W, 16384, seed=42)
+    r = O.update(prm, TS, start, mode=O.FAITHFUL, want_affected=True)
+    out = e.update(p3.Engine.make_params(**prm), TS, start)
+    assert r["affected"].sum() > 0
+    assert_parity(out, r["out"], W, what="faithful at 16k")
+    e.close()
