@@ -373,3 +373,23 @@ def test_faithful_mode_reproduces_the_reference_quirk(default_params, kernel):
     assert r["affected"].sum() > 0
     assert_parity(out, r["out"], W, what="faithful at 16k")
     e.close()
+
+
+# ---------------------------------------------------------------- the compiled host mirror (C++)
+def test_cpp_host_mirror_headless_stepper(default_params):
+    """host/particle_3d.hpp + host/headless.cpp: the compiled-language mirror of the crate API drives the
+    same C ABI; config 1 (default scene, 100 steps) must land on the oracle's kinetic energy."""
+    import json
+    import subprocess
+
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "3d-particle-simulation-_b200")
+    subprocess.run(["make", "-C", pkg, "headless"], check=True, capture_output=True)
+    g = np.load(os.path.join(GOLD, "default_scene_n1000_seed42.npz"))
+    for per_step in ("1", "0"):  # update() every step (main.rs:199) and the device-resident run
+        r = subprocess.run([os.path.join(pkg, "headless"), "1000", "100", "42", per_step], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out = json.loads(r.stdout)
+        assert abs(out["ke"] - g["ideal_ke"][-1]) / g["ideal_ke"][-1] < 1e-4
+    # n = 0 scales the box to W = 0 < 2r: the mirror must "panic" like assert! at src/lib.rs:132 (exit code 101)
+    bad = subprocess.run([os.path.join(pkg, "headless"), "0", "1"], capture_output=True, text=True)
+    assert bad.returncode == 101 and "world_size" in bad.stderr
