@@ -47,7 +47,7 @@ int fail(int code, const char *fmt, ...) {
 constexpr int kMaxTimedSteps = 512;
 constexpr int kEv = 5;  // events per timed step
 constexpr int kRefTile = 128;       // threads per CTA of the reference-order kernel
-constexpr int kPairAutoMin = 4096;  // P3D_FORCE_AUTO switches to the pair kernel from this n
+constexpr int kCellsAutoMin = 512;  // P3D_FORCE_AUTO uses the cell list from this n, the reference-order kernel below
 
 template <typename T>
 struct DevBuf {
@@ -300,7 +300,9 @@ int launch_unpack(p3d_engine *e, size_t n) {
 }
 
 int resolve_force_kernel_for(const p3d_engine *e, size_t n) {
-    if (e->opt_force == P3D_FORCE_AUTO) return n >= (size_t)kPairAutoMin ? P3D_FORCE_PAIR : P3D_FORCE_REFERENCE_ORDER;
+    // AUTO: the cell list (same results, O(N * neighbours) work; falls back to all-pairs inside
+    // launch_force when the box is narrower than three cells); tiny systems take the exact kernel.
+    if (e->opt_force == P3D_FORCE_AUTO) return n >= (size_t)kCellsAutoMin ? P3D_FORCE_CELLS : P3D_FORCE_REFERENCE_ORDER;
     return e->opt_force;
 }
 int resolve_force_kernel(const p3d_engine *e) { return resolve_force_kernel_for(e, e->n); }
@@ -445,8 +447,27 @@ int launch_force(p3d_engine *e, const DevParams &P) {
         // box narrower than three cells: the all-pairs path below handles it
     }
     // --- pair path ---
-    if (!e->typed)
-        return fail(P3D_ERR_INVALID, "the pair kernel needs the type-grouped layout: set the force kernel before p3d_upload");
+    if (!e->typed) {
+        if (kind != P3D_FORCE_CELLS)
+            return fail(P3D_ERR_INVALID, "the pair kernel needs the type-grouped layout: set the force kernel before p3d_upload");
+        // cell list requested but the box is narrower than three cells: all pairs with the exact kernel
+        CU(cudaMemsetAsync(flag_next, 0, sizeof(int), st));
+        if (e->step_ev) {
+            CU(cudaEventRecord(e->step_ev[1], st));
+            CU(cudaEventRecord(e->step_ev[2], st));
+        }
+        const int per = ((e->M + e->world - 1) / e->world) * e->B;
+        const int i0 = std::min(ns, e->rank * per), i1 = std::min(ns, i0 + per);
+        if (e->world > 1) CU(cudaMemsetAsync(e->frc.p, 0, (size_t)ns * sizeof(float4), st));
+        if (i1 > i0) {
+            k_force_ref<kRefTile><<<(i1 - i0 + kRefTile - 1) / kRefTile, kRefTile, ref_smem(kRefTile, P.T), st>>>(
+                pos, ns, i0, i1, e->frc.p, P, e->matrix.p, flag_cur, -1);
+            e->counters[0]++;
+            e->counters[1]++;
+        }
+        CU(cudaGetLastError());
+        return P3D_OK;  // (K5 needs the cell list, which this box is too narrow for)
+    }
     const int B = e->B;
     const float margin = std::max(1.0e-3f, 1.0e-5f * P.W);
     const float interior_limit = e->opt_block_sort ? (P.half - P.reach - margin) : -1.0f;

@@ -266,13 +266,27 @@ def test_particles_update_semantics(default_params):
 def test_auto_kernel_selection_and_counters(eng, default_params):
     eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_AUTO)
     c0 = eng.counters()
-    eng.update(p3.Engine.make_params(**default_params), TS, p3.generate_particles(10.0, 1000, seed=1))
+    eng.update(p3.Engine.make_params(**default_params), TS, p3.generate_particles(10.0, 300, seed=1))
     c1 = eng.counters()
-    assert c1["force"] - c0["force"] == 1 and c1["integrate"] - c0["integrate"] == 1
+    assert c1["force"] - c0["force"] == 1 and c1["integrate"] - c0["integrate"] == 1  # reference-order kernel
     prm = dict(default_params, world_size=20.0)
-    eng.update(p3.Engine.make_params(**prm), TS, p3.generate_particles(20.0, 8000, seed=1))
+    start = p3.generate_particles(20.0, 8000, seed=1)
+    out = eng.update(p3.Engine.make_params(**prm), TS, start)
     c2 = eng.counters()
-    assert c2["force"] - c1["force"] == 2  # pair kernel + boundary x boundary kernel
+    assert c2["force"] - c1["force"] == 1  # the cell-list kernel
+    assert_parity(out, O.update(prm, TS, start, mode=O.IDEAL)["out"], 20.0)
+    eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_PAIR)
+    eng.update(p3.Engine.make_params(**prm), TS, start)
+    c3 = eng.counters()
+    assert c3["force"] - c2["force"] == 2  # pair kernel + boundary x boundary kernel
+    # a box narrower than three cells: AUTO / CELLS fall back to all pairs and still match
+    eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_AUTO)
+    prm = dict(default_params, world_size=4.0, particle_effect_radius=2.0, min_pull_ratio=0.3)
+    small = p3.generate_particles(4.0, 700, seed=3)
+    prm2 = dict(prm, world_size=2.5, particle_effect_radius=1.25)
+    small2 = p3.generate_particles(2.5, 700, seed=3)
+    assert_parity(eng.update(p3.Engine.make_params(**prm2), TS, small2), O.update(prm2, TS, small2, mode=O.IDEAL)["out"], 2.5)
+    assert_parity(eng.update(p3.Engine.make_params(**prm), TS, small), O.update(prm, TS, small, mode=O.IDEAL)["out"], 4.0)
 
 
 # ---------------------------------------------------------------- size-independent properties at scale
