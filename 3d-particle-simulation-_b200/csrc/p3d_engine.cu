@@ -111,7 +111,6 @@ struct p3d_engine {
     int opt_timing = 0;
     int opt_block_sort = 1;
     int opt_faithful = 0;    // K5: add the reference's bucket double-visit contributions
-    int opt_tune = 0;        // developer knob: kernel variant selection for experiments
 
     // sharding
     int rank = 0, world = 1;
@@ -632,11 +631,13 @@ int p3d_create(int device, p3d_engine **out) {
     if (prop.major != 10)
         return fail(P3D_ERR_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major,
                     prop.minor);
+    cudaStream_t stream = nullptr;
+    CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     p3d_engine *e = new p3d_engine();
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
-    e->stream = e->own_stream;
+    e->own_stream = stream;
+    e->stream = stream;
     *out = e;
     return P3D_OK;
 }
@@ -677,7 +678,6 @@ int p3d_set_option(p3d_engine *e, int option, int value) {
         case P3D_OPT_TIMING: e->opt_timing = value ? 1 : 0; return P3D_OK;
         case P3D_OPT_BLOCK_SORT: e->opt_block_sort = value ? 1 : 0; return P3D_OK;
         case P3D_OPT_FAITHFUL: e->opt_faithful = value ? 1 : 0; return P3D_OK;
-        case 99: e->opt_tune = value; return P3D_OK;
         case P3D_OPT_BLOCK_SIZE:
             if (value != 0 && value != 128 && value != 256) return fail(P3D_ERR_INVALID, "block size must be 0 (auto), 128 or 256");
             e->B_next = value;
@@ -889,6 +889,8 @@ int p3d_shard_force(p3d_engine *e, const p3d_params *prm) {
     int rc;
     if ((rc = canonicalise(prm, P))) return rc;
     if (e->n_slots == 0) return fail(P3D_ERR_INVALID, "no particles uploaded");
+    if (prm->id_count != e->T)
+        return fail(P3D_ERR_INVALID, "id_count %u differs from the uploaded layout (%u): upload again", prm->id_count, e->T);
     CU(cudaSetDevice(e->device));
     if ((rc = upload_matrix(e, prm))) return rc;
     // the out-of-box flag written by this rank's integrate covers only its own shard; after the

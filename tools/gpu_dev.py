@@ -70,7 +70,6 @@ def timing(n, W, kernel, steps=3, plummer=False, block=0, tune=0):
     eng.set_option(_abi.OPT_FORCE_KERNEL, kernel)
     eng.set_option(_abi.OPT_TIMING, 1)
     eng.set_option(_abi.OPT_BLOCK_SIZE, block)
-    eng.set_option(99, tune)
     P = p3.Engine.make_params(**prm)
     eng.upload(parts, 5)
     eng.step(P, 1 / 60, 1)
