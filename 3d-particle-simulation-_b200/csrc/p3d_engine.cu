@@ -486,10 +486,10 @@ int launch_force(p3d_engine *e, const DevParams &P) {
     const int rows = (M - e->rank + e->world - 1) / e->world;  // rows rank, rank+world, ...
     if (rows > 0) {
         // One warp per CTA: every per-block-pair scalar is then provably warp-uniform and lives in
-        // uniform registers (no register-file reads in the FFMA2 stream).  ~24 waves of 16 CTAs/SM
+        // uniform registers (no register-file reads in the FFMA2 stream).  ~128 waves of 16 CTAs/SM
         // keep the tail of the last wave small; never more warps than offsets in a row.
         const int offsets = M / 2 + 1;
-        int splits = (int)std::min<long long>(offsets, std::max<long long>(1, (24LL * 16 * e->sm_count + rows - 1) / rows));
+        int splits = (int)std::min<long long>(offsets, std::max<long long>(1, (128LL * 16 * e->sm_count + rows - 1) / rows));
         const dim3 grid((unsigned)rows * (unsigned)splits);
         const float *sx = e->sx.p, *sy = e->sy.p, *sz = e->sz.p;
 #define P3D_PAIR_ARGS sx, sy, sz, e->sidx.p, e->bclass.p, e->seg_type.p, M, e->rank, e->world, splits, e->frc.p, P, e->matrix.p, flag_cur
