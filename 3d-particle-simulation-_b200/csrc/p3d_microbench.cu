@@ -216,10 +216,61 @@ __global__ void __launch_bounds__(128) mb_rf(float *out, int iters, float a, flo
     if (acc == 123.456f) out[0] = acc;
 }
 
+// The pair kernel's packed instruction stream with its real dataflow (8 i-particles per lane against one
+// j register pair per coordinate, both accumulators), used to attribute cycles to operand forms.
+// V bit 0: real MUFU.RSQ (else inv = d2);  bit 1: real FMNMX clamps (else pass-through);
+// bit 2: drop the j-side accumulation (sji + 3 FFMA2);  bit 3: drop the i-side accumulation;
+// bit 4: i-positions as register PAIRS instead of broadcast scalars;  bit 5: drop the three FADD2.
+template <int V>
+__global__ void __launch_bounds__(32, 16) mb_pack(float *out, int iters, float a, float b) {
+    constexpr int R = 8;
+    float nix[R], niy[R], niz[R];
+    float2 aix[R], aiy[R], aiz[R];
+    float2 jx = make_float2(a + threadIdx.x, a - threadIdx.x), jy = make_float2(b + threadIdx.x, 2.f * b), jz = make_float2(a, b);
+    float2 ajx = make_float2(0.f, 0.f), ajy = ajx, ajz = ajx;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        nix[r] = a * (r + 1) + threadIdx.x; niy[r] = b * (r + 2); niz[r] = a + b * r;
+        aix[r] = aiy[r] = aiz[r] = make_float2(0.f, 0.f);
+    }
+    const float2 c2 = make_float2(a * 2.8f, a * 2.8f), ncm = make_float2(-b, -b), nc2 = make_float2(-a, -a),
+                 im = make_float2(3.3f * a, 3.3f * a), neg1 = make_float2(-1.f, -1.f), tiny = make_float2(1e-30f, 1e-30f);
+    const float2 aij = make_float2(out[1], out[1]), aji = make_float2(out[2], out[2]);  // uniform loads
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float2 dx, dy, dz;
+            if (V & 32) { dx = jx; dy = jy; dz = jz; }
+            else if (V & 16) { dx = __fadd2_rn(jx, make_float2(nix[r], niy[r])); dy = __fadd2_rn(jy, make_float2(niy[r], niz[r])); dz = __fadd2_rn(jz, make_float2(niz[r], nix[r])); }
+            else { dx = __fadd2_rn(jx, make_float2(nix[r], nix[r])); dy = __fadd2_rn(jy, make_float2(niy[r], niy[r])); dz = __fadd2_rn(jz, make_float2(niz[r], niz[r])); }
+            float2 d2 = __ffma2_rn(dx, dx, tiny);
+            d2 = __ffma2_rn(dy, dy, d2);
+            d2 = __ffma2_rn(dz, dz, d2);
+            const float2 inv = (V & 1) ? make_float2(rsq(d2.x), rsq(d2.y)) : d2;
+            const float2 p1 = __ffma2_rn(inv, ncm, c2), p2 = __ffma2_rn(inv, c2, nc2);
+            float2 ti = (V & 2) ? make_float2(fmaxf(fminf(p1.x, p2.x), 0.f), fmaxf(fminf(p1.y, p2.y), 0.f)) : __fadd2_rn(p1, p2);
+            float2 rs = __ffma2_rn(inv, neg1, im);
+            if (V & 2) rs = make_float2(fminf(rs.x, 0.f), fminf(rs.y, 0.f));
+            const float2 sij = __ffma2_rn(aij, ti, rs);
+            if (!(V & 8)) { aix[r] = __ffma2_rn(dx, sij, aix[r]); aiy[r] = __ffma2_rn(dy, sij, aiy[r]); aiz[r] = __ffma2_rn(dz, sij, aiz[r]); }
+            else { ajx = __fadd2_rn(ajx, sij); }
+            if (!(V & 4)) {
+                const float2 sji = __ffma2_rn(aji, ti, rs);
+                ajx = __ffma2_rn(dx, sji, ajx); ajy = __ffma2_rn(dy, sji, ajy); ajz = __ffma2_rn(dz, sji, ajz);
+            }
+        }
+        jx.x += 1e-3f;  // keep the loop body from being hoisted
+    }
+    float acc = ajx.x + ajx.y + ajy.x + ajy.y + ajz.x + ajz.y;
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc += aix[r].x + aix[r].y + aiy[r].x + aiy[r].y + aiz[r].x + aiz[r].y;
+    if (acc == 123.456f) out[0] = acc;
+}
+
 }  // namespace
 
 extern "C" int p3d_microbench(int device, int kind, int iters, double out[4]) {
-    if (!out || iters <= 0 || kind < 0 || kind > 17) return P3D_ERR_INVALID;
+    if (!out || iters <= 0 || kind < 0 || kind > 17 + 64) return P3D_ERR_INVALID;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
         cudaGetLastError();
@@ -244,6 +295,7 @@ extern "C" int p3d_microbench(int device, int kind, int iters, double out[4]) {
     if (kind == 3) { threads = 128; ctas_per_sm = 4; lane_fma_per_thread = (double)iters * 8 * 68 * 2; }
     if (kind >= 4) { threads = 128; ctas_per_sm = 4; lane_fma_per_thread = (double)iters * 16; }  // bodies per thread
     if (kind >= 13) lane_fma_per_thread = (double)iters * 8;  // reps per thread (8 FFMA2 each; kind 17: 12 FFMA2 + 12 FFMA)
+    if (kind >= 18) { threads = 32; ctas_per_sm = 16; lane_fma_per_thread = (double)iters * 8; }  // pair-packs per thread
     const int grid = sms * ctas_per_sm;
     for (int rep = 0; rep < 2; ++rep) {  // first launch warms up
         cudaEventRecord(e0);
@@ -265,6 +317,19 @@ extern "C" int p3d_microbench(int device, int kind, int iters, double out[4]) {
         if (kind == 15) mb_rf<2><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
         if (kind == 16) mb_rf<3><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
         if (kind == 17) mb_rf<4><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 18 + 0) mb_pack<0><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 18 + 1) mb_pack<1><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 18 + 2) mb_pack<2><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 18 + 3) mb_pack<3><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 18 + 4) mb_pack<4><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 18 + 7) mb_pack<7><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 18 + 8) mb_pack<8><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 18 + 11) mb_pack<11><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 18 + 12) mb_pack<12><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 18 + 16) mb_pack<16><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 18 + 19) mb_pack<19><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 18 + 35) mb_pack<35><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 18 + 32) mb_pack<32><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
         if (kind == 12) mb_generic<17, 0, 0, 0, 0><<<grid, threads>>>(d, iters, 0.999f, 0.001f);  // FFMA2 only
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return P3D_ERR_CUDA; }

@@ -122,8 +122,22 @@ def micro3():
         print(f"micro3 [{names[kind]}]: rc={rc} {out[1]:.2f} ms -> {cyc:.2f} SMSP-cycles per body", flush=True)
 
 
+def micro4():
+    L = _abi.load()
+    names = {0: "F2 stream only (17 F2)", 1: "+MUFU", 2: "+FMNMX", 3: "+MUFU +FMNMX (= kernel body)", 4: "F2 only, no j-side (13 F2)",
+             7: "kernel body, no j-side", 8: "F2 only, no i-side (14 F2 + 1 FADD2)", 11: "kernel body, no i-side", 12: "F2 only, no accumulation (11 F2)",
+             16: "F2 only, i-positions as pairs", 19: "kernel body, i-positions as pairs", 32: "F2 only, no FADD2 (14 F2)", 35: "kernel body, no FADD2"}
+    for v in sorted(names):
+        out = (C.c_double * 4)()
+        rc = L.p3d_microbench(0, 18 + v, 4000, out)
+        cyc = out[3] * 1e6 * out[2] * 4 / (out[0] / 32)
+        print(f"micro4 [{names[v]:40s}] rc={rc} -> {cyc:6.2f} SMSP-cycles per pair-pack", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["parity", "timing", "micro"]
+    if "micro4" in what:
+        micro4()
     if "micro3" in what:
         micro3()
     if "micro" in what:
