@@ -111,6 +111,13 @@ struct p3d_engine {
     int opt_timing = 0;
     int opt_block_sort = 1;
     int opt_faithful = 0;    // K5: add the reference's bucket double-visit contributions
+    int opt_graph = 1;       // replay device-resident multi-step runs through a CUDA graph (two steps per graph)
+
+    // CUDA graph of two consecutive steps (returns cur/parity to their starting values)
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<unsigned char> graph_key;
+    uint64_t graph_launches[3] = {0, 0, 0};  // kernel / force / integrate launches inside one replay
+    uint64_t layout_version = 0;
 
     // sharding
     int rank = 0, world = 1;
@@ -193,6 +200,7 @@ int build_layout_identity(p3d_engine *e, size_t n, uint32_t T) {
     e->n = n;
     e->T = T;
     e->typed = false;
+    e->layout_version++;
     int rc;
     if ((rc = ensure_common(e, n, ns))) return rc;
     CU(cudaMemsetAsync(e->flags.p, 0, 4 * sizeof(int), e->stream));
@@ -202,6 +210,7 @@ int build_layout_identity(p3d_engine *e, size_t n, uint32_t T) {
 int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T) {
     if (n > (size_t)0x7fff0000) return fail(P3D_ERR_INVALID, "n too large");
     e->typed = true;
+    e->layout_version++;
     e->B = e->B_next ? e->B_next : (n >= 65536 ? 256 : 128);
     const int B = e->B;
     std::vector<size_t> count(T, 0);
@@ -583,26 +592,100 @@ int check_box_now(p3d_engine *e, const DevParams &P) {
     return P3D_OK;
 }
 
+int one_step(p3d_engine *e, const DevParams &P, float ts, bool timed, int s) {
+    int rc;
+    e->step_ev = timed ? &e->ev[(size_t)kEv * s] : nullptr;
+    if (timed) CU(cudaEventRecord(e->step_ev[0], e->stream));
+    if ((rc = launch_force(e, P))) { e->step_ev = nullptr; return rc; }
+    if (timed) CU(cudaEventRecord(e->step_ev[3], e->stream));
+    if ((rc = launch_integrate(e, P, ts))) { e->step_ev = nullptr; return rc; }
+    if (timed) {
+        CU(cudaEventRecord(e->step_ev[4], e->stream));
+        e->timed_steps = s + 1;
+    }
+    e->step_ev = nullptr;
+    e->cur ^= 1;
+    e->parity ^= 1;
+    return P3D_OK;
+}
+
+void drop_graph(p3d_engine *e) {
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    e->graph_exec = nullptr;
+    e->graph_key.clear();
+}
+
+// Everything a captured pair of steps depends on; any change forces a re-capture.
+std::vector<unsigned char> make_graph_key(const p3d_engine *e, const DevParams &P, float ts) {
+    std::vector<unsigned char> k(sizeof(DevParams) + sizeof(float) + 8 * sizeof(uint64_t));
+    unsigned char *p = k.data();
+    std::memcpy(p, &P, sizeof(DevParams)); p += sizeof(DevParams);
+    std::memcpy(p, &ts, sizeof(float)); p += sizeof(float);
+    const uint64_t v[8] = {e->layout_version, (uint64_t)e->cur, (uint64_t)e->parity, (uint64_t)resolve_force_kernel(e),
+                           (uint64_t)e->opt_faithful, (uint64_t)e->opt_block_sort, (uint64_t)(uintptr_t)e->stream,
+                           (uint64_t)e->rank * 64 + (uint64_t)e->world};
+    std::memcpy(p, v, sizeof(v));
+    return k;
+}
+
+// Captures two consecutive steps on the engine stream.  Must run after at least one ordinary step with
+// the same configuration, so that every lazily allocated buffer already exists (no cudaMalloc in capture).
+int capture_two_steps(p3d_engine *e, const DevParams &P, float ts) {
+    drop_graph(e);
+    const uint64_t before[3] = {e->counters[0], e->counters[1], e->counters[2]};
+    if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return P3D_ERR_CUDA;  // e.g. the legacy default stream cannot be captured: caller steps normally
+    }
+    int rc = one_step(e, P, ts, false, 0);
+    if (!rc) rc = one_step(e, P, ts, false, 0);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+    for (int k = 0; k < 3; ++k) {
+        e->graph_launches[k] = e->counters[k] - before[k];
+        e->counters[k] = before[k];  // nothing ran yet
+    }
+    if (rc || ce != cudaSuccess || !graph) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        return rc ? rc : P3D_ERR_CUDA;
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+        cudaGetLastError();
+        e->graph_exec = nullptr;
+        return P3D_ERR_CUDA;
+    }
+    e->graph_key = make_graph_key(e, P, ts);
+    return P3D_OK;
+}
+
 int run_steps(p3d_engine *e, const p3d_params *prm, const DevParams &P, float ts, int n_steps) {
     int rc;
     if ((rc = upload_matrix(e, prm))) return rc;
     if ((rc = check_box_now(e, P))) return rc;  // world_size may have changed since the last call
     e->timed_steps = 0;
     if (e->opt_timing && (rc = ensure_events(e, n_steps))) return rc;
-    for (int s = 0; s < n_steps; ++s) {
-        const bool timed = e->opt_timing && s < kMaxTimedSteps;
-        e->step_ev = timed ? &e->ev[(size_t)kEv * s] : nullptr;
-        if (timed) CU(cudaEventRecord(e->step_ev[0], e->stream));
-        if ((rc = launch_force(e, P))) { e->step_ev = nullptr; return rc; }
-        if (timed) CU(cudaEventRecord(e->step_ev[3], e->stream));
-        if ((rc = launch_integrate(e, P, ts))) { e->step_ev = nullptr; return rc; }
-        if (timed) {
-            CU(cudaEventRecord(e->step_ev[4], e->stream));
-            e->timed_steps = s + 1;
+    int s = 0;
+    // Long untimed runs replay a two-step CUDA graph: a step is 8-15 launches, and at small N their
+    // launch latency is the whole step time.
+    if (e->opt_graph && !e->opt_timing && n_steps >= 6) {
+        for (; s < 2; ++s)
+            if ((rc = one_step(e, P, ts, false, s))) return rc;  // allocates every lazily created buffer
+        if (!e->graph_exec || e->graph_key != make_graph_key(e, P, ts)) {
+            if (capture_two_steps(e, P, ts) != P3D_OK) drop_graph(e);  // fall back to ordinary launches
         }
-        e->step_ev = nullptr;
-        e->cur ^= 1;
-        e->parity ^= 1;
+        if (e->graph_exec) {
+            for (; s + 2 <= n_steps; s += 2) {
+                CU(cudaGraphLaunch(e->graph_exec, e->stream));
+                for (int k = 0; k < 3; ++k) e->counters[k] += e->graph_launches[k];
+            }
+        }
+    }
+    for (; s < n_steps; ++s) {
+        const bool timed = e->opt_timing && s < kMaxTimedSteps;
+        if ((rc = one_step(e, P, ts, timed, s))) return rc;
     }
     return P3D_OK;
 }
@@ -656,6 +739,7 @@ void p3d_destroy(p3d_engine *e) {
     for (auto &b : e->cvals) b.release();
     e->cell_start.release(); e->cell_end.release(); e->cpos.release(); e->cub_tmp.release();
     e->aos.release(); e->fout.release(); e->sx.release(); e->sy.release(); e->sz.release(); e->matrix.release(); e->flags.release(); e->diag.release();
+    drop_graph(e);
     for (auto x : e->ev) cudaEventDestroy(x);
     for (auto x : e->ev_call) if (x) cudaEventDestroy(x);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -678,6 +762,7 @@ int p3d_set_option(p3d_engine *e, int option, int value) {
         case P3D_OPT_TIMING: e->opt_timing = value ? 1 : 0; return P3D_OK;
         case P3D_OPT_BLOCK_SORT: e->opt_block_sort = value ? 1 : 0; return P3D_OK;
         case P3D_OPT_FAITHFUL: e->opt_faithful = value ? 1 : 0; return P3D_OK;
+        case P3D_OPT_GRAPH: e->opt_graph = value ? 1 : 0; return P3D_OK;
         case P3D_OPT_BLOCK_SIZE:
             if (value != 0 && value != 128 && value != 256) return fail(P3D_ERR_INVALID, "block size must be 0 (auto), 128 or 256");
             e->B_next = value;
@@ -694,6 +779,7 @@ int p3d_get_option(p3d_engine *e, int option, int *value) {
         case P3D_OPT_BLOCK_SORT: *value = e->opt_block_sort; return P3D_OK;
         case P3D_OPT_BLOCK_SIZE: *value = e->B_next; return P3D_OK;
         case P3D_OPT_FAITHFUL: *value = e->opt_faithful; return P3D_OK;
+        case P3D_OPT_GRAPH: *value = e->opt_graph; return P3D_OK;
         default: return fail(P3D_ERR_INVALID, "unknown option %d", option);
     }
 }

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_PKG_ROOT, "libp3d.so")
 OK, ERR_WORLD_TOO_SMALL, ERR_BAD_ID, ERR_CUDA, ERR_INVALID, ERR_NO_DEVICE = 0, 1, 2, 3, 4, 5
 MAX_TYPES = 64
 # options
-OPT_FORCE_KERNEL, OPT_TIMING, OPT_BLOCK_SORT, OPT_BLOCK_SIZE, OPT_FAITHFUL = 0, 1, 3, 4, 5
+OPT_FORCE_KERNEL, OPT_TIMING, OPT_GRAPH, OPT_BLOCK_SORT, OPT_BLOCK_SIZE, OPT_FAITHFUL = 0, 1, 2, 3, 4, 5
 FORCE_AUTO, FORCE_REFERENCE_ORDER, FORCE_PAIR, FORCE_CELLS = 0, 1, 2, 3
 BUF_POS, BUF_POS_NEXT, BUF_VEL, BUF_FORCE = 0, 1, 2, 3
 

@@ -87,7 +87,7 @@ int p3d_diagnostics(p3d_engine *eng, double out[8]);
 enum p3d_option {
     P3D_OPT_FORCE_KERNEL = 0, /* see p3d_force_kernel */
     P3D_OPT_TIMING = 1,       /* 1: record CUDA events around each kernel of a step */
-    /* 2 is reserved */
+    P3D_OPT_GRAPH = 2,        /* 1 (default): untimed p3d_step runs of >= 6 steps replay a two-step CUDA graph */
     P3D_OPT_BLOCK_SORT = 3,   /* 1: re-partition interior/boundary blocks every step (fast path) */
     P3D_OPT_FAITHFUL = 5,     /* 1: reproduce the reference's bucket double-visit quirk: after the
                                  ideal force pass a correction kernel adds (multiplicity - 1) x contribution for every

@@ -407,3 +407,29 @@ def test_cpp_host_mirror_headless_stepper(default_params):
     # n = 0 scales the box to W = 0 < 2r: the mirror must "panic" like assert! at src/lib.rs:132 (exit code 101)
     bad = subprocess.run([os.path.join(pkg, "headless"), "0", "1"], capture_output=True, text=True)
     assert bad.returncode == 101 and "world_size" in bad.stderr
+
+
+# ---------------------------------------------------------------- CUDA-graph replay of multi-step runs
+@pytest.mark.parametrize("kernel", KERNELS, ids=IDS)
+def test_graph_replay_matches_ordinary_launches(default_params, kernel):
+    W = 16.0
+    prm = dict(default_params, world_size=W)
+    start = p3.generate_particles(W, 4096, seed=7)
+    P = p3.Engine.make_params(**prm)
+    outs = []
+    for graph in (1, 0):
+        e = p3.Engine(0)
+        e.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+        e.set_option(_abi.OPT_GRAPH, graph)
+        e.upload(start, 5)
+        e.step(P, TS, 15)   # odd count: two eager steps, six replays, one eager step
+        e.step(P, TS, 8)    # second call: the graph is re-captured for the flipped buffers
+        outs.append(e.download())
+        c = e.counters()
+        assert c["integrate"] == 23
+        e.close()
+    if kernel == _abi.FORCE_PAIR:  # float atomics: summation order differs run to run
+        dv, dp = parity_errors(outs[0], outs[1], W)
+        assert dv.max() < 1e-4 and dp.max() < 1e-4
+    else:
+        assert outs[0].tobytes() == outs[1].tobytes()

@@ -153,6 +153,18 @@ if __name__ == "__main__":
         parity(16384, 25.4, _abi.FORCE_PAIR, walls=True, acceleration=(0.0, -1.0, 0.0))
         parity(16384, 25.4, _abi.FORCE_PAIR, particle_effect_radius=0.8)
         parity(20000, 64.0, _abi.FORCE_PAIR, plummer=True)
+    if "graph" in what:
+        for n, W in ((1000, 10.0), (16384, 25.4), (262144, 64.0), (1048576, 101.6)):
+            for kernel in (_abi.FORCE_CELLS, _abi.FORCE_REFERENCE_ORDER) if n == 1000 else (_abi.FORCE_CELLS,):
+                for graph in (0, 1):
+                    prm = p3.default_params_dict(); prm["world_size"] = W
+                    eng = p3.Engine(0); eng.set_option(_abi.OPT_FORCE_KERNEL, kernel); eng.set_option(_abi.OPT_GRAPH, graph)
+                    P = p3.Engine.make_params(**prm)
+                    eng.upload(p3.generate_particles(W, n, 42), 5)
+                    eng.step(P, 1 / 60, 10); eng.sync()
+                    t0 = time.time(); eng.step(P, 1 / 60, 400); eng.sync(); dt = (time.time() - t0) / 400
+                    print(f"graph={graph} n={n} kernel={kernel}: {dt*1e6:.1f} us/step", flush=True)
+                    eng.close()
     if "cells" in what:
         timing(1000, 10.0, _abi.FORCE_CELLS, steps=50)
         timing(16384, 25.4, _abi.FORCE_CELLS, steps=50)
