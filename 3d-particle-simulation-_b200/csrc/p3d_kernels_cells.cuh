@@ -100,18 +100,26 @@ __global__ void __launch_bounds__(128) k_force_cells(const float4 *__restrict__ 
             float py = pi.y;
             if (ny < 0) { ny += nc; py = pyp; }
             else if (ny >= nc) { ny -= nc; py = pym; }
-#pragma unroll 1
+            // the three cells of this row: fetch their ranges together (independent loads in flight)
+            uint32_t s0[3], s1[3];
+            float pxs[3];
+#pragma unroll
             for (int dx = -1; dx <= 1; ++dx) {
                 int nx = cx + dx;
                 float px = pi.x;
                 if (nx < 0) { nx += nc; px = pxp; }
                 else if (nx >= nc) { nx -= nc; px = pxm; }
                 const uint32_t c = (uint32_t)((nz * nc + ny) * nc + nx);
-                const uint32_t s0 = cell_start[c];
-                if (s0 == 0xFFFFFFFFu) continue;
-                const uint32_t s1 = cell_end[c];
-                for (uint32_t j = s0; j < s1; ++j) {
-                    const float4 q = cpos[j];
+                s0[dx + 1] = __ldg(cell_start + c);
+                s1[dx + 1] = __ldg(cell_end + c);
+                pxs[dx + 1] = px;
+            }
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                if (s0[t] == 0xFFFFFFFFu) continue;
+                const float px = pxs[t];
+                for (uint32_t j = s0[t]; j < s1[t]; ++j) {
+                    const float4 q = __ldg(cpos + j);
                     const float rx = __fsub_rn(q.x, px), ry = __fsub_rn(q.y, py), rz = __fsub_rn(q.z, pz);
                     const float d2 = fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, 1.0e-30f)));
                     const float inv = rsqrt_approx(d2);
