@@ -94,7 +94,7 @@ struct p3d_engine {
     DevBuf<int> seg_start, seg_end, cnt;
     DevBuf<int2> cta_cnt, cta_off;
     // cell-list path
-    DevBuf<uint32_t> ckeys[2], cvals[2], cell_start, cell_end;
+    DevBuf<uint32_t> ckeys[2], cvals[2], cell_off;
     DevBuf<float4> cpos;
     DevBuf<unsigned char> cub_tmp;
     DevBuf<float> aos, fout, sx, sy, sz;
@@ -340,20 +340,18 @@ int build_cells(p3d_engine *e, const DevParams &P, const float4 *pos, int *flag_
         if ((rc = e->cvals[k].ensure((size_t)ns))) return rc;
     }
     if ((rc = e->cpos.ensure((size_t)ns))) return rc;
-    if ((rc = e->cell_start.ensure(ncell + 1))) return rc;
-    if ((rc = e->cell_end.ensure(ncell + 1))) return rc;
+    if ((rc = e->cell_off.ensure(ncell + 2))) return rc;
     int end_bit = 1;
     while ((1ull << end_bit) <= ncell) ++end_bit;
     size_t tmp_bytes = 0;
     CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, e->ckeys[0].p, e->ckeys[1].p, e->cvals[0].p, e->cvals[1].p,
                                        ns, 0, end_bit, st));
     if ((rc = e->cub_tmp.ensure(tmp_bytes))) return rc;
-    CU(cudaMemsetAsync(e->cell_start.p, 0xFF, (ncell + 1) * sizeof(uint32_t), st));
     k_cell_keys<<<(ns + 255) / 256, 256, 0, st>>>(pos, ns, g, e->ckeys[0].p, e->cvals[0].p, flag_to_clear);
     CU(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp_bytes, e->ckeys[0].p, e->ckeys[1].p, e->cvals[0].p,
                                        e->cvals[1].p, ns, 0, end_bit, st));
-    k_cell_gather<<<(ns + 255) / 256, 256, 0, st>>>(pos, ns, e->ckeys[1].p, e->cvals[1].p, e->cpos.p,
-                                                   e->cell_start.p, e->cell_end.p);
+    k_cell_gather<<<(ns + 255) / 256, 256, 0, st>>>(pos, ns, e->ckeys[1].p, e->cvals[1].p, e->cpos.p, e->cell_off.p,
+                                                   (uint32_t)ncell);
     e->counters[0] += 3;
     CU(cudaGetLastError());
     return P3D_OK;
@@ -368,12 +366,12 @@ int launch_quirk(p3d_engine *e, const DevParams &P, const CellGrid &g, const int
         const size_t sm = (size_t)P.T * P.T * sizeof(float);
         if (P.rcut)
             k_quirk_correction<true><<<(i1 - i0 + 127) / 128, 128, sm, e->stream>>>(
-                e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_start.p, e->cell_end.p, i0, i1, g, e->frc.p, P,
-                e->matrix.p, flag_cur, (unsigned long long)e->n);
+                e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_off.p, i0, i1, g, e->frc.p, P, e->matrix.p, flag_cur,
+                (unsigned long long)e->n);
         else
             k_quirk_correction<false><<<(i1 - i0 + 127) / 128, 128, sm, e->stream>>>(
-                e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_start.p, e->cell_end.p, i0, i1, g, e->frc.p, P,
-                e->matrix.p, flag_cur, (unsigned long long)e->n);
+                e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_off.p, i0, i1, g, e->frc.p, P, e->matrix.p, flag_cur,
+                (unsigned long long)e->n);
         e->counters[0]++;
     }
     CU(cudaGetLastError());
@@ -429,13 +427,13 @@ int launch_force(p3d_engine *e, const DevParams &P) {
             if (i1 > i0) {
                 const size_t sm = (size_t)P.T * P.T * sizeof(float);
                 if (P.rcut)
-                    k_force_cells<true><<<(i1 - i0 + 127) / 128, 128, sm, st>>>(
-                        e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_start.p, e->cell_end.p, ns, i0, i1, g,
-                        e->frc.p, P, e->matrix.p, flag_cur);
+                    k_force_cells<true><<<(i1 - i0 + kCellThreads - 1) / kCellThreads, kCellThreads, sm, st>>>(
+                        e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_off.p, ns, i0, i1, g, e->frc.p, P, e->matrix.p,
+                        flag_cur);
                 else
-                    k_force_cells<false><<<(i1 - i0 + 127) / 128, 128, sm, st>>>(
-                        e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_start.p, e->cell_end.p, ns, i0, i1, g,
-                        e->frc.p, P, e->matrix.p, flag_cur);
+                    k_force_cells<false><<<(i1 - i0 + kCellThreads - 1) / kCellThreads, kCellThreads, sm, st>>>(
+                        e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_off.p, ns, i0, i1, g, e->frc.p, P, e->matrix.p,
+                        flag_cur);
                 e->counters[0]++;
                 e->counters[1]++;
             }
@@ -737,7 +735,7 @@ void p3d_destroy(p3d_engine *e) {
     e->seg_start.release(); e->seg_end.release(); e->cnt.release(); e->cta_cnt.release(); e->cta_off.release();
     for (auto &b : e->ckeys) b.release();
     for (auto &b : e->cvals) b.release();
-    e->cell_start.release(); e->cell_end.release(); e->cpos.release(); e->cub_tmp.release();
+    e->cell_off.release(); e->cpos.release(); e->cub_tmp.release();
     e->aos.release(); e->fout.release(); e->sx.release(); e->sy.release(); e->sz.release(); e->matrix.release(); e->flags.release(); e->diag.release();
     drop_graph(e);
     for (auto x : e->ev) cudaEventDestroy(x);

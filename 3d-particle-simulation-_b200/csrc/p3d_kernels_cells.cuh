@@ -44,33 +44,67 @@ __global__ void __launch_bounds__(256) k_cell_keys(const float4 *__restrict__ po
     vals[s] = (uint32_t)s;
 }
 
-// After the sort: gather positions into cell order and mark where each cell starts.
-// cell_start has nc^3 + 1 entries, pre-filled with 0xFFFFFFFF ("empty") by a memset.
+// After the sort: gather positions into cell order and build cell_off[c] = first sorted index whose
+// key is >= c, for c = 0 .. nc^3 (so cell c occupies [cell_off[c], cell_off[c+1]), empty cells included,
+// and cell_off[nc^3] is where the ghosts start).  The thread that sees a key change fills the gap.
 __global__ void __launch_bounds__(256) k_cell_gather(const float4 *__restrict__ pos, int n_slots,
                                                      const uint32_t *__restrict__ keys_sorted,
                                                      const uint32_t *__restrict__ vals_sorted,
-                                                     float4 *__restrict__ cpos, uint32_t *__restrict__ cell_start,
-                                                     uint32_t *__restrict__ cell_end) {
+                                                     float4 *__restrict__ cpos, uint32_t *__restrict__ cell_off,
+                                                     uint32_t n_cells) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_slots) return;
     const uint32_t key = keys_sorted[k];
     cpos[k] = pos[vals_sorted[k]];
-    if (k == 0 || keys_sorted[k - 1] != key) cell_start[key] = (uint32_t)k;
-    if (k == n_slots - 1 || keys_sorted[k + 1] != key) cell_end[key] = (uint32_t)(k + 1);
+    const uint32_t first = (k == 0) ? 0u : keys_sorted[k - 1] + 1u;
+    for (uint32_t c = first; c <= key; ++c) cell_off[c] = (uint32_t)k;  // no iterations when the key repeats
+    if (k == n_slots - 1)
+        for (uint32_t c = key + 1u; c <= n_cells; ++c) cell_off[c] = (uint32_t)n_slots;
+}
+
+// One candidate of the cell list: the reference's relative position (src/lib.rs:211-212) and the
+// branch-free force law of k_force_pair.
+template <bool RCUT>
+__device__ __forceinline__ void cell_pair(const float4 q, float px, float py, float pz, const float *arow, float c2,
+                                          float ncm, float nc2, float im, float r2, float &ax, float &ay, float &az) {
+    const float rx = __fsub_rn(q.x, px), ry = __fsub_rn(q.y, py), rz = __fsub_rn(q.z, pz);
+    const float d2 = fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, 1.0e-30f)));
+    const float inv = rsqrt_approx(d2);
+    const float p1 = fmaf(inv, ncm, c2), p2 = fmaf(inv, c2, nc2);
+    float ti = fmaxf(fminf(p1, p2), 0.0f);
+    float rs = fminf(im - inv, 0.0f);
+    if (RCUT) {
+        if (!(d2 < r2)) { ti = 0.0f; rs = 0.0f; }
+    }
+    const float s = fmaf(arow[f2u(q.w)], ti, rs);
+    ax = fmaf(rx, s, ax);
+    ay = fmaf(ry, s, ay);
+    az = fmaf(rz, s, az);
 }
 
 // One thread per particle in cell order.  i_begin/i_end shard the sorted range across GPUs.
+//
+// The candidates of a particle are up to 18 contiguous runs of the sorted array: for each of the 9
+// (dy,dz) rows the cells cx-1..cx+1 that do not wrap form ONE run (cells are x-fastest), plus one
+// single-cell run when the row wraps through an x face.  The runs are written to shared memory and
+// consumed by a single flat loop, so a warp iterates max-over-lanes(total candidates) times instead of
+// sum-over-cells(max-over-lanes(cell population)) — with ~1 particle per cell that is ~40 vs ~100.
+constexpr int kCellThreads = 128;
+constexpr int kCellRuns = 18;
+
 template <bool RCUT>
-__global__ void __launch_bounds__(128) k_force_cells(const float4 *__restrict__ cpos,
-                                                     const uint32_t *__restrict__ keys_sorted,
-                                                     const uint32_t *__restrict__ vals_sorted,
-                                                     const uint32_t *__restrict__ cell_start,
-                                                     const uint32_t *__restrict__ cell_end, int n_slots, int i_begin,
-                                                     int i_end, CellGrid g, float4 *__restrict__ frc, DevParams P,
-                                                     const float *__restrict__ matrix,
-                                                     const int *__restrict__ flags) {
+__global__ void __launch_bounds__(kCellThreads) k_force_cells(const float4 *__restrict__ cpos,
+                                                              const uint32_t *__restrict__ keys_sorted,
+                                                              const uint32_t *__restrict__ vals_sorted,
+                                                              const uint32_t *__restrict__ cell_off, int n_slots,
+                                                              int i_begin, int i_end, CellGrid g,
+                                                              float4 *__restrict__ frc, DevParams P,
+                                                              const float *__restrict__ matrix,
+                                                              const int *__restrict__ flags) {
     if (flags[0] != 0) return;  // out-of-box input: the reference-order kernel takes the step
     extern __shared__ float smat_dyn[];
+    __shared__ uint32_t run_lo[kCellRuns][kCellThreads], run_hi[kCellRuns][kCellThreads];
+    __shared__ uint8_t run_img[kCellRuns][kCellThreads];  // 2 bits per axis: 0 = offset 0, 1 = +W, 2 = -W
     for (int k = threadIdx.x; k < P.T * P.T; k += blockDim.x) smat_dyn[k] = matrix[k];
     __syncthreads();
     const int k = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,60 +117,68 @@ __global__ void __launch_bounds__(128) k_force_cells(const float4 *__restrict__ 
               cz = (int)(key / (uint32_t)(nc * nc));
     const float *arow = smat_dyn + f2u(pi.w) * (uint32_t)P.T;
     const float c2 = P.c2, ncm = -P.c2 * P.m, nc2 = -P.c2, im = P.inv_m, r2 = P.r2;
-    // `position + offset` for offset = -W and +W (src/lib.rs:190-192), rounded like the reference
-    const float pxm = __fadd_rn(pi.x, -P.W), pxp = __fadd_rn(pi.x, P.W);
-    const float pym = __fadd_rn(pi.y, -P.W), pyp = __fadd_rn(pi.y, P.W);
-    const float pzm = __fadd_rn(pi.z, -P.W), pzp = __fadd_rn(pi.z, P.W);
-    float ax = 0.f, ay = 0.f, az = 0.f;
-#pragma unroll 1
+    const int t = threadIdx.x;
+
+    int n_runs = 0;
+#pragma unroll
     for (int dz = -1; dz <= 1; ++dz) {
-        int nz = cz + dz;
-        float pz = pi.z;
-        if (nz < 0) { nz += nc; pz = pzp; }        // neighbour lies through the -z face: it sees us at z + W
-        else if (nz >= nc) { nz -= nc; pz = pzm; }
-#pragma unroll 1
+        int nz = cz + dz, iz = 0;
+        if (nz < 0) { nz += nc; iz = 1; } else if (nz >= nc) { nz -= nc; iz = 2; }
+#pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
-            int ny = cy + dy;
-            float py = pi.y;
-            if (ny < 0) { ny += nc; py = pyp; }
-            else if (ny >= nc) { ny -= nc; py = pym; }
-            // the three cells of this row: fetch their ranges together (independent loads in flight)
-            uint32_t s0[3], s1[3];
-            float pxs[3];
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                int nx = cx + dx;
-                float px = pi.x;
-                if (nx < 0) { nx += nc; px = pxp; }
-                else if (nx >= nc) { nx -= nc; px = pxm; }
-                const uint32_t c = (uint32_t)((nz * nc + ny) * nc + nx);
-                s0[dx + 1] = __ldg(cell_start + c);
-                s1[dx + 1] = __ldg(cell_end + c);
-                pxs[dx + 1] = px;
-            }
-#pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                if (s0[t] == 0xFFFFFFFFu) continue;
-                const float px = pxs[t];
-                for (uint32_t j = s0[t]; j < s1[t]; ++j) {
-                    const float4 q = __ldg(cpos + j);
-                    const float rx = __fsub_rn(q.x, px), ry = __fsub_rn(q.y, py), rz = __fsub_rn(q.z, pz);
-                    const float d2 = fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, 1.0e-30f)));
-                    const float inv = rsqrt_approx(d2);
-                    const float p1 = fmaf(inv, ncm, c2), p2 = fmaf(inv, c2, nc2);
-                    float ti = fmaxf(fminf(p1, p2), 0.0f);
-                    float rs = fminf(im - inv, 0.0f);
-                    if (RCUT) {
-                        if (!(d2 < r2)) { ti = 0.0f; rs = 0.0f; }
-                    }
-                    const float s = fmaf(arow[f2u(q.w)], ti, rs);
-                    ax = fmaf(rx, s, ax);
-                    ay = fmaf(ry, s, ay);
-                    az = fmaf(rz, s, az);
-                }
+            int ny = cy + dy, iy = 0;
+            if (ny < 0) { ny += nc; iy = 1; } else if (ny >= nc) { ny -= nc; iy = 2; }
+            const uint32_t row = (uint32_t)((nz * nc + ny) * nc);
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, nc - 1);
+            run_lo[n_runs][t] = __ldg(cell_off + row + x0);
+            run_hi[n_runs][t] = __ldg(cell_off + row + x1 + 1);
+            run_img[n_runs][t] = (uint8_t)(iy << 2 | iz << 4);
+            ++n_runs;
+            if (cx == 0) {  // the -x neighbour is the last cell of the row; it sees us at x + W
+                run_lo[n_runs][t] = __ldg(cell_off + row + nc - 1);
+                run_hi[n_runs][t] = __ldg(cell_off + row + nc);
+                run_img[n_runs][t] = (uint8_t)(1 | iy << 2 | iz << 4);
+                ++n_runs;
+            } else if (cx == nc - 1) {
+                run_lo[n_runs][t] = __ldg(cell_off + row);
+                run_hi[n_runs][t] = __ldg(cell_off + row + 1);
+                run_img[n_runs][t] = (uint8_t)(2 | iy << 2 | iz << 4);
+                ++n_runs;
             }
         }
     }
+    // `position + offset` for offset = +W / -W (src/lib.rs:190-192), rounded like the reference
+    const float sx3[3] = {pi.x, __fadd_rn(pi.x, P.W), __fadd_rn(pi.x, -P.W)};
+    const float sy3[3] = {pi.y, __fadd_rn(pi.y, P.W), __fadd_rn(pi.y, -P.W)};
+    const float sz3[3] = {pi.z, __fadd_rn(pi.z, P.W), __fadd_rn(pi.z, -P.W)};
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    int run = -1;
+    uint32_t j = 0, hi = 0;
+    float px = pi.x, py = pi.y, pz = pi.z;
+    for (;;) {
+        while (j >= hi) {  // next non-empty run
+            if (++run >= n_runs) goto done;
+            j = run_lo[run][t];
+            hi = run_hi[run][t];
+            const int img = run_img[run][t];
+            const int ix = img & 3, iy = (img >> 2) & 3, iz = (img >> 4) & 3;
+            px = ix == 0 ? sx3[0] : (ix == 1 ? sx3[1] : sx3[2]);
+            py = iy == 0 ? sy3[0] : (iy == 1 ? sy3[1] : sy3[2]);
+            pz = iz == 0 ? sz3[0] : (iz == 1 ? sz3[1] : sz3[2]);
+        }
+        if (hi - j >= 8u) {  // long run (dense region): four candidates per trip, loads issued together
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = __ldg(cpos + j + u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cell_pair<RCUT>(q[u], px, py, pz, arow, c2, ncm, nc2, im, r2, ax, ay, az);
+            j += 4;
+            continue;
+        }
+        cell_pair<RCUT>(__ldg(cpos + j), px, py, pz, arow, c2, ncm, nc2, im, r2, ax, ay, az);
+        ++j;
+    }
+done:
     frc[vals_sorted[k]] = make_float4(ax, ay, az, 0.f);
 }
 
@@ -182,8 +224,7 @@ template <bool RCUT>
 __global__ void __launch_bounds__(128) k_quirk_correction(const float4 *__restrict__ cpos,
                                                           const uint32_t *__restrict__ keys_sorted,
                                                           const uint32_t *__restrict__ vals_sorted,
-                                                          const uint32_t *__restrict__ cell_start,
-                                                          const uint32_t *__restrict__ cell_end, int i_begin,
+                                                          const uint32_t *__restrict__ cell_off, int i_begin,
                                                           int i_end, CellGrid g, float4 *__restrict__ frc,
                                                           DevParams P, const float *__restrict__ matrix,
                                                           const int *__restrict__ flags, unsigned long long n_hash) {
@@ -222,9 +263,7 @@ __global__ void __launch_bounds__(128) k_quirk_correction(const float4 *__restri
                 float px = pi.x;
                 if (nx < 0) { nx += nc; px = pxp; } else if (nx >= nc) { nx -= nc; px = pxm; }
                 const uint32_t c = (uint32_t)((nz * nc + ny) * nc + nx);
-                const uint32_t s0 = cell_start[c];
-                if (s0 == 0xFFFFFFFFu) continue;
-                const uint32_t s1 = cell_end[c];
+                const uint32_t s0 = cell_off[c], s1 = cell_off[c + 1];
                 for (uint32_t j = s0; j < s1; ++j) {
                     const float4 q = cpos[j];
                     const float rx = __fsub_rn(q.x, px), ry = __fsub_rn(q.y, py), rz = __fsub_rn(q.z, pz);
