@@ -77,6 +77,8 @@ struct p3d_engine {
     int sm_count = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr;               // boundary-x-boundary kernel runs beside the pair kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     // layout
     size_t n = 0;        // live particles
@@ -498,6 +500,27 @@ int launch_force(p3d_engine *e, const DevParams &P) {
         const int offsets = M / 2 + 1;
         int splits = (int)std::min<long long>(offsets, std::max<long long>(1, (128LL * 16 * e->sm_count + rows - 1) / rows));
         const dim3 grid((unsigned)rows * (unsigned)splits);
+        // boundary x boundary kernel: forked onto the auxiliary stream so that it runs beside the pair
+        // kernel (both only add into frc).  Its j-blocks are split over enough CTAs to fill the machine;
+        // only BOUNDARY rows do work and their number is known on the device only, so it is estimated from
+        // the boundary shell volume of a uniform cloud (a clustered cloud has fewer and merely over-splits).
+        const double shell = 1.0 - std::pow(std::max(0.0, 1.0 - 2.0 * (double)P.reach / (double)P.W), 3.0);
+        const long long est_rows = std::max<long long>(P.T, (long long)(shell * rows) + P.T);
+        const int jsplit = (int)std::max<long long>(1, std::min<long long>(64, (8LL * e->sm_count + est_rows - 1) / est_rows));
+        const dim3 bgrid((unsigned)rows, (unsigned)jsplit);
+        cudaStream_t ax = e->aux_stream;
+        CU(cudaEventRecord(e->ev_fork, st));
+        CU(cudaStreamWaitEvent(ax, e->ev_fork, 0));
+#define P3D_BXB_ARGS e->spos.p, e->sidx.p, e->bclass.p, M, e->rank, e->world, e->seg_start.p, e->seg_end.p, e->cnt.p, e->frc.p, P, e->matrix.p, flag_cur
+        if (B == 128) {
+            if (P.rcut) k_force_bxb<128, true><<<bgrid, 128, ref_smem(128, P.T), ax>>>(P3D_BXB_ARGS);
+            else        k_force_bxb<128, false><<<bgrid, 128, ref_smem(128, P.T), ax>>>(P3D_BXB_ARGS);
+        } else {
+            if (P.rcut) k_force_bxb<256, true><<<bgrid, 256, ref_smem(256, P.T), ax>>>(P3D_BXB_ARGS);
+            else        k_force_bxb<256, false><<<bgrid, 256, ref_smem(256, P.T), ax>>>(P3D_BXB_ARGS);
+        }
+#undef P3D_BXB_ARGS
+        CU(cudaEventRecord(e->ev_join, ax));
         const float *sx = e->sx.p, *sy = e->sy.p, *sz = e->sz.p;
 #define P3D_PAIR_ARGS sx, sy, sz, e->sidx.p, e->bclass.p, e->seg_type.p, M, e->rank, e->world, splits, e->frc.p, P, e->matrix.p, flag_cur
         if (B == 128) {
@@ -509,22 +532,7 @@ int launch_force(p3d_engine *e, const DevParams &P) {
         }
 #undef P3D_PAIR_ARGS
         if (e->step_ev) CU(cudaEventRecord(e->step_ev[2], st));
-        // boundary x boundary: split the j-blocks of a row over enough CTAs to fill the machine
-        // (only BOUNDARY rows do work; their number is known on the device only, so estimate it from the
-        //  boundary shell volume of a uniform cloud — a clustered cloud has fewer and merely over-splits)
-        const double shell = 1.0 - std::pow(std::max(0.0, 1.0 - 2.0 * (double)P.reach / (double)P.W), 3.0);
-        const long long est_rows = std::max<long long>(P.T, (long long)(shell * rows) + P.T);
-        const int jsplit = (int)std::max<long long>(1, std::min<long long>(64, (8LL * e->sm_count + est_rows - 1) / est_rows));
-        const dim3 bgrid((unsigned)rows, (unsigned)jsplit);
-#define P3D_BXB_ARGS e->spos.p, e->sidx.p, e->bclass.p, M, e->rank, e->world, e->seg_start.p, e->seg_end.p, e->cnt.p, e->frc.p, P, e->matrix.p, flag_cur
-        if (B == 128) {
-            if (P.rcut) k_force_bxb<128, true><<<bgrid, 128, ref_smem(128, P.T), st>>>(P3D_BXB_ARGS);
-            else        k_force_bxb<128, false><<<bgrid, 128, ref_smem(128, P.T), st>>>(P3D_BXB_ARGS);
-        } else {
-            if (P.rcut) k_force_bxb<256, true><<<bgrid, 256, ref_smem(256, P.T), st>>>(P3D_BXB_ARGS);
-            else        k_force_bxb<256, false><<<bgrid, 256, ref_smem(256, P.T), st>>>(P3D_BXB_ARGS);
-        }
-#undef P3D_BXB_ARGS
+        CU(cudaStreamWaitEvent(st, e->ev_join, 0));  // join
         e->counters[0] += 2;
         e->counters[1] += 2;
     }
@@ -712,9 +720,20 @@ int p3d_create(int device, p3d_engine **out) {
     if (prop.major != 10)
         return fail(P3D_ERR_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major,
                     prop.minor);
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    // highest priority: its few CTAs are placed as soon as slots free up, instead of queueing behind the
+    // tens of thousands of pair-kernel CTAs
+    CU(cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, prio_hi));
+    CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     p3d_engine *e = new p3d_engine();
+    e->aux_stream = aux;
+    e->ev_fork = ev_fork;
+    e->ev_join = ev_join;
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
     e->own_stream = stream;
@@ -740,6 +759,9 @@ void p3d_destroy(p3d_engine *e) {
     drop_graph(e);
     for (auto x : e->ev) cudaEventDestroy(x);
     for (auto x : e->ev_call) if (x) cudaEventDestroy(x);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }

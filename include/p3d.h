@@ -109,7 +109,8 @@ int p3d_get_option(p3d_engine *eng, int option, int *value);
  * events on the engine stream, milliseconds summed over the timed steps of that call:
  * [0]=whole force pass [1]=integrate kernel [2]=pack (upload side) [3]=unpack (download side)
  * [4]=partition kernels + force memset [5]=h2d copy [6]=d2h copy [7]=force+integrate
- * [8]=pair kernel alone [9]=boundary-x-boundary (+ out-of-box fallback) kernels [10]=timed steps [11]=0 */
+ * [8]=pair kernel (the boundary-x-boundary kernel runs beside it on an auxiliary stream) [9]=what remains of the
+ * boundary-x-boundary kernel after the pair kernel ended (+ out-of-box fallback) [10]=timed steps [11]=0 */
 int p3d_get_timing(p3d_engine *eng, float ms[12]);
 /* Launch counters since creation: [0]=kernels launched, [1]=force kernels, [2]=integrate kernels. */
 int p3d_get_counters(p3d_engine *eng, uint64_t out[4]);
