@@ -433,3 +433,17 @@ def test_graph_replay_matches_ordinary_launches(default_params, kernel):
         assert dv.max() < 1e-4 and dp.max() < 1e-4
     else:
         assert outs[0].tobytes() == outs[1].tobytes()
+
+
+# ---------------------------------------------------------------- roofline denominator
+def test_fp32_microbenchmark_confirms_the_roofline_denominator():
+    """The FP32 roofline uses 148 SMs x 128 lanes x 2 flop x clock; the packed-FFMA2 microbenchmark must
+    reach it (and must not exceed it: FFMA2 halves issue slots, it does not double throughput)."""
+    import ctypes as C
+
+    out = (C.c_double * 4)()
+    assert _abi.load().p3d_microbench(0, 1, 2000, out) == 0
+    peak = out[2] * 128 * out[3] * 1e6  # lane-FMA/s at the maximum SM clock
+    assert 0.90 <= out[0] / peak <= 1.02, out[0] / peak
+    assert _abi.load().p3d_microbench(0, 0, 2000, out) == 0  # scalar FFMA: same datapath, a bit lower
+    assert 0.80 <= out[0] / peak <= 1.02
