@@ -434,7 +434,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--particles", "--n", dest="n", type=int, default=N_DEFAULT,
+                    help="particle count (use --particles under torch.distributed.run: its parser trips over --n)")
     ap.add_argument("--world-size", type=float, default=None, help="box edge W (default: density 1)")
     ap.add_argument("--block", type=int, default=0, choices=[0, 128, 256], help="0 = engine default")
     ap.add_argument("--e2e-steps", type=int, default=3)
