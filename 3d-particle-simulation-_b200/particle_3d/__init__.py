@@ -227,6 +227,22 @@ class Particles:
         return new.copy()  # src/lib.rs:271 clone
 
 
+def _particles_run(self, ts: float, n_steps: int) -> np.ndarray:
+    """n_steps x update(ts) with the state resident in HBM (one upload, one download): what a headless run
+    wants.  Equivalent to calling update() n_steps times; past_particles is the state before the LAST step
+    only when n_steps == 1, otherwise it is the state before the run."""
+    eng = self.engine
+    before = self.active_particles
+    eng.upload(before, self.id_count)
+    eng.step(self._params(), ts, n_steps)
+    self.active_particles = eng.download()
+    self.past_particles = before
+    return self.active_particles.copy()
+
+
+Particles.run = _particles_run
+
+
 def default_scene(n: int = 1000, seed: int = 42, device: int = 0) -> Particles:
     """The default scene of src/bin/main.rs:123-148 with a seeded generator."""
     lib = _abi.load()

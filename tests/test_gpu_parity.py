@@ -263,6 +263,15 @@ def test_particles_update_semantics(default_params):
     assert_parity(ret, O.update(prm, TS, before, mode=O.IDEAL)["out"], 10.0)
 
 
+def test_particles_run_equals_repeated_update(default_params):
+    a = p3.default_scene(n=2000, seed=9)
+    b = p3.default_scene(n=2000, seed=9)
+    for _ in range(12):
+        a.update(TS)
+    out = b.run(TS, 12)  # device-resident, replayed through the CUDA graph
+    assert out.tobytes() == a.active_particles.tobytes()
+
+
 def test_auto_kernel_selection_and_counters(eng, default_params):
     eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_AUTO)
     c0 = eng.counters()
