@@ -1,0 +1,58 @@
+"""bench.py's driver contract, as far as it can be checked without a GPU: the reference arm runs on the CPU
+and prints exactly one JSON line with the agreed keys; the engine arm refuses to run without a device."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args, env=None):
+    e = dict(os.environ, **(env or {}))
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, env=e,
+                          timeout=600)
+
+
+def test_reference_arm_prints_one_json_line():
+    r = _run("--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "3", "--particles", "20000")
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "pair_interactions_per_s" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["value"] == 20000.0 ** 2 / (d["ms_per_step"] * 1e-3)
+    assert "workload" in d["config"]
+
+
+def test_reference_arm_non_zero_ranks_exit_quietly_and_ignore_omp_threads():
+    r = _run("--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "3", "--particles", "5000",
+             env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "3", "--particles", "5000", env={"OMP_NUM_THREADS": "1"})
+    d = json.loads(r.stdout.strip())
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))  # torchrun's OMP_NUM_THREADS=1 must not throttle it
+
+
+def test_engine_arm_fails_loudly_without_a_gpu():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            import pytest
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    r = _run("--steps", "1", "--warmup", "3", "--particles", "4096", "--no-cpu")
+    assert r.returncode != 0  # no CPU fallback
+
+
+def test_graft_entry_points_exist():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+
+    assert callable(g.build) and callable(g.smoke)
