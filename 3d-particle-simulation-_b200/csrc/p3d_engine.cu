@@ -523,13 +523,17 @@ int launch_force(p3d_engine *e, const DevParams &P) {
         CU(cudaEventRecord(e->ev_join, ax));
         const float *sx = e->sx.p, *sy = e->sy.p, *sz = e->sz.p;
 #define P3D_PAIR_ARGS sx, sy, sz, e->sidx.p, e->bclass.p, e->seg_type.p, M, e->rank, e->world, splits, e->frc.p, P, e->matrix.p, flag_cur
+        // MPOS: min_pull_ratio > 0 lets the kernel fold c2*m into the matrix scalars (one FFMA2 fewer per pack)
+        const bool mpos = P.m > 0.0f && P.m < 1.0f;
+#define P3D_PAIR_LAUNCH(R_, RC_, MP_) k_force_pair<R_, RC_, 16, 1, MP_><<<grid, 32, 0, st>>>(P3D_PAIR_ARGS)
         if (B == 128) {
-            if (P.rcut) k_force_pair<4, true, 16, 1><<<grid, 32, 0, st>>>(P3D_PAIR_ARGS);
-            else        k_force_pair<4, false, 16, 1><<<grid, 32, 0, st>>>(P3D_PAIR_ARGS);
+            if (P.rcut) { if (mpos) P3D_PAIR_LAUNCH(4, true, true); else P3D_PAIR_LAUNCH(4, true, false); }
+            else        { if (mpos) P3D_PAIR_LAUNCH(4, false, true); else P3D_PAIR_LAUNCH(4, false, false); }
         } else {
-            if (P.rcut) k_force_pair<8, true, 16, 1><<<grid, 32, 0, st>>>(P3D_PAIR_ARGS);
-            else        k_force_pair<8, false, 16, 1><<<grid, 32, 0, st>>>(P3D_PAIR_ARGS);
+            if (P.rcut) { if (mpos) P3D_PAIR_LAUNCH(8, true, true); else P3D_PAIR_LAUNCH(8, true, false); }
+            else        { if (mpos) P3D_PAIR_LAUNCH(8, false, true); else P3D_PAIR_LAUNCH(8, false, false); }
         }
+#undef P3D_PAIR_LAUNCH
 #undef P3D_PAIR_ARGS
         if (e->step_ev) CU(cudaEventRecord(e->step_ev[2], st));
         CU(cudaStreamWaitEvent(st, e->ev_join, 0));  // join

@@ -188,8 +188,10 @@ struct PairConsts {
     float2 ncm;    // -c2*m
     float2 nc2;    // -c2
     float2 im;     // 1/m (or +inf)
+    float2 nim;    // -1/m
     float2 neg1;   // -1
     float2 tiny;   // 1e-30: keeps rsqrt finite at d2 == 0 (self pair, coincident particles)
+    float c2m;     // c2*m: folded into the matrix scalars when m > 0 (see pair_pack, MPOS)
 };
 
 __device__ __forceinline__ PairConsts make_pair_consts(const DevParams &P) {
@@ -198,7 +200,9 @@ __device__ __forceinline__ PairConsts make_pair_consts(const DevParams &P) {
     c.ncm = dup2(-P.c2 * P.m);
     c.nc2 = dup2(-P.c2);
     c.im = dup2(P.inv_m);
+    c.nim = dup2(-P.inv_m);
     c.neg1 = dup2(-1.0f);
+    c.c2m = P.c2 * P.m;
     c.tiny = dup2(1.0e-30f);
     return c;
 }
@@ -208,7 +212,7 @@ __device__ __forceinline__ PairConsts make_pair_consts(const DevParams &P) {
 // duplication.  17 packed FP32 instructions + 2 MUFU.RSQ + 6 FMNMX for four ordered interactions.
 // The accumulation order alternates i/j so that consecutive FFMA2 share a source register pair
 // (operand-reuse cache): an FFMA2 that reads three distinct register pairs costs 3 cycles, not 2.
-template <bool RCUT, bool SYM>
+template <bool RCUT, bool SYM, bool MPOS>
 __device__ __forceinline__ void pair_pack(const float2 jx, const float2 jy, const float2 jz, const float nix,
                                           const float niy, const float niz, const PairConsts &c,
                                           const float2 aij, const float2 aji, const float r2, float2 &aix,
@@ -220,10 +224,16 @@ __device__ __forceinline__ void pair_pack(const float2 jx, const float2 jy, cons
     d2 = __ffma2_rn(dy, dy, d2);
     d2 = __ffma2_rn(dz, dz, d2);
     const float2 inv = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
-    const float2 p1 = __ffma2_rn(inv, c.ncm, c.c2);   // c2 * (1 - m/d)
-    const float2 p2 = __ffma2_rn(inv, c.c2, c.nc2);   // c2 * (1/d - 1)
-    float2 ti = make_float2(fmaxf(fminf(p1.x, p2.x), 0.0f), fmaxf(fminf(p1.y, p2.y), 0.0f));
-    float2 rs = __ffma2_rn(inv, c.neg1, c.im);        // 1/m - 1/d
+    float2 rs = __ffma2_rn(inv, c.neg1, c.im);        // u = 1/m - 1/d
+    float2 ti;
+    if (MPOS) {
+        const float2 p2 = __ffma2_rn(inv, c.im, c.nim);   // (1/d - 1) / m
+        ti = make_float2(fmaxf(fminf(rs.x, p2.x), 0.0f), fmaxf(fminf(rs.y, p2.y), 0.0f));
+    } else {
+        const float2 p1 = __ffma2_rn(inv, c.ncm, c.c2);   // c2 * (1 - m/d)
+        const float2 p2 = __ffma2_rn(inv, c.c2, c.nc2);   // c2 * (1/d - 1)
+        ti = make_float2(fmaxf(fminf(p1.x, p2.x), 0.0f), fmaxf(fminf(p1.y, p2.y), 0.0f));
+    }
     rs = make_float2(fminf(rs.x, 0.0f), fminf(rs.y, 0.0f));
     if (RCUT) {  // r < 1: src/lib.rs:216-220 cuts inside the force range
         if (!(d2.x < r2)) { ti.x = 0.0f; rs.x = 0.0f; }
@@ -253,7 +263,7 @@ __device__ __forceinline__ void atomic_add_f3(float4 *dst, float x, float y, flo
 // K1 (fast): symmetric block-pair force pass.  grid.x = n_rows * splits, block = NW warps.
 // Row a (row_begin + k*row_stride: the multi-GPU shard takes every world-th row) owns the block
 // pairs {a, a+o mod M}, o in [0, M/2]; the warps of the `splits` CTAs of a row interleave over o.
-template <int R, bool RCUT, int MINB, int NW>
+template <int R, bool RCUT, int MINB, int NW, bool MPOS>
 __global__ void __launch_bounds__(32 * NW, MINB)
 k_force_pair(const float *__restrict__ sx, const float *__restrict__ sy, const float *__restrict__ sz,
              const uint32_t *__restrict__ sidx,
@@ -295,8 +305,9 @@ k_force_pair(const float *__restrict__ sx, const float *__restrict__ sy, const f
         if (cb == P3D_BLK_EMPTY) continue;
         if (ca == P3D_BLK_BOUNDARY && cb == P3D_BLK_BOUNDARY) continue;  // -> k_force_bxb
         const int tb = btype[b];
-        const float2 aij = dup2(matrix[ta * P.T + tb]);
-        const float2 aji = dup2(matrix[tb * P.T + ta]);
+        const float ascale = MPOS ? c.c2m : 1.0f;
+        const float2 aij = dup2(matrix[ta * P.T + tb] * ascale);
+        const float2 aji = dup2(matrix[tb * P.T + ta] * ascale);
         const bool diag = (o == 0);
 #pragma unroll 1
         for (int round = 0; round < ROUNDS; ++round) {
@@ -309,7 +320,7 @@ k_force_pair(const float *__restrict__ sx, const float *__restrict__ sy, const f
             for (int step = 0; step < 32; ++step) {
 #pragma unroll
                 for (int r = 0; r < R; ++r)
-                    pair_pack<RCUT, true>(jx, jy, jz, nix[r], niy[r], niz[r], c, aij, aji, P.r2, aix[r], aiy[r],
+                    pair_pack<RCUT, true, MPOS>(jx, jy, jz, nix[r], niy[r], niz[r], c, aij, aji, P.r2, aix[r], aiy[r],
                                           aiz[r], ajx, ajy, ajz);
                 jx = shfl2(jx, next); jy = shfl2(jy, next); jz = shfl2(jz, next);
                 ajx = shfl2(ajx, next); ajy = shfl2(ajy, next); ajz = shfl2(ajz, next);
