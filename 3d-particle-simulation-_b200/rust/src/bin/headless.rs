@@ -6,15 +6,25 @@ fn main() {
     let n: usize = std::env::args().nth(1).and_then(|s| s.parse().ok()).unwrap_or(1000);
     let steps: usize = std::env::args().nth(2).and_then(|s| s.parse().ok()).unwrap_or(100);
     // splitmix64, the same stream as p3d_scene_uniform (csrc/p3d_scene.cpp)
-    let mut s: u64 = 42;
-    let mut next = move || { s = s.wrapping_add(0x9E3779B97F4A7C15); let mut z = s;
-        z = (z ^ (z >> 30)).wrapping_mul(0xBF58476D1CE4E5B9); z = (z ^ (z >> 27)).wrapping_mul(0x94D049BB133111EB); z ^ (z >> 31) };
+    struct SplitMix(u64);
+    impl SplitMix {
+        fn next(&mut self) -> u64 {
+            self.0 = self.0.wrapping_add(0x9E3779B97F4A7C15);
+            let mut z = self.0;
+            z = (z ^ (z >> 30)).wrapping_mul(0xBF58476D1CE4E5B9);
+            z = (z ^ (z >> 27)).wrapping_mul(0x94D049BB133111EB);
+            z ^ (z >> 31)
+        }
+        fn unit(&mut self) -> f32 { (self.next() >> 40) as f32 * (1.0 / 16_777_216.0) }
+    }
+    let mut rng = SplitMix(42);
     let world = 10.0f32;
-    let mut unit = || (next() >> 40) as f32 * (1.0 / 16_777_216.0);
     let mut parts = Vec::with_capacity(n);
     for _ in 0..n {
-        let (x, y, z) = (-5.0 + world * unit(), -5.0 + world * unit(), -5.0 + world * unit());
-        let id = (next() % 5) as u32;
+        let x = -5.0 + world * rng.unit();
+        let y = -5.0 + world * rng.unit();
+        let z = -5.0 + world * rng.unit();
+        let id = (rng.next() % 5) as u32;
         parts.push(Particle { position: cgmath::vec3(x, y, z), velocity: cgmath::vec3(0.0, 0.0, 0.0), id });
     }
     let mut sim = Particles {
