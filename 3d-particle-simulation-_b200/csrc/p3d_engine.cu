@@ -100,6 +100,7 @@ struct p3d_engine {
     DevBuf<float4> cpos;
     DevBuf<unsigned char> cub_tmp;
     DevBuf<float> aos, fout, sx, sy, sz;
+    DevBuf<float4> render;
     DevBuf<float> matrix;
     DevBuf<int> flags;      // [0],[1]: out-of-box flags (double-buffered by step parity)
     DevBuf<double> diag;
@@ -759,7 +760,7 @@ void p3d_destroy(p3d_engine *e) {
     for (auto &b : e->ckeys) b.release();
     for (auto &b : e->cvals) b.release();
     e->cell_off.release(); e->cpos.release(); e->cub_tmp.release();
-    e->aos.release(); e->fout.release(); e->sx.release(); e->sy.release(); e->sz.release(); e->matrix.release(); e->flags.release(); e->diag.release();
+    e->aos.release(); e->fout.release(); e->render.release(); e->sx.release(); e->sy.release(); e->sz.release(); e->matrix.release(); e->flags.release(); e->diag.release();
     drop_graph(e);
     for (auto x : e->ev) cudaEventDestroy(x);
     for (auto x : e->ev_call) if (x) cudaEventDestroy(x);
@@ -885,6 +886,31 @@ int p3d_download(p3d_engine *e, p3d_particle *out, size_t n) {
         CU(cudaEventElapsedTime(&e->last_ms[3], e->ev_call[3], e->ev_call[4]));
         CU(cudaEventElapsedTime(&e->last_ms[6], e->ev_call[4], e->ev_call[5]));
     }
+    return P3D_OK;
+}
+
+int p3d_download_render(p3d_engine *e, float world_size, void *out, size_t out_bytes, size_t n) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (n != e->n) return fail(P3D_ERR_INVALID, "n=%zu but %zu particles are resident", n, e->n);
+    if (!out || out_bytes < 16 + 32 * n) return fail(P3D_ERR_INVALID, "render buffer needs %zu bytes", 16 + 32 * n);
+    // header of WGSL `struct Particles` (src/bin/particles.wgsl:8-12): world_size f32 @0, length u32 @4,
+    // the runtime array starts at its 16-byte alignment
+    unsigned char *o = static_cast<unsigned char *>(out);
+    std::memset(o, 0, 16);
+    std::memcpy(o, &world_size, 4);
+    const uint32_t len = (uint32_t)n;
+    std::memcpy(o + 4, &len, 4);
+    if (!n) return P3D_OK;
+    CU(cudaSetDevice(e->device));
+    int rc;
+    if ((rc = e->render.ensure(2 * n))) return rc;
+    k_unpack_render<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->pos[e->cur].p, e->vel.p,
+                                                                        e->typed ? e->slot_of.p : nullptr,
+                                                                        e->render.p, (int)n);
+    e->counters[0]++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(o + 16, e->render.p, 32 * n, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
     return P3D_OK;
 }
 

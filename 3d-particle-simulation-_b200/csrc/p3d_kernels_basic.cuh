@@ -71,6 +71,21 @@ __global__ void __launch_bounds__(256) k_unpack(const float4 *__restrict__ pos, 
     for (int w = threadIdx.x; w < cnt * 7; w += 256) dst[w] = sm[w];
 }
 
+// SoA slots -> the render storage buffer of the reference app: WGSL
+// `array<Particle>` with `position: vec3<f32>` @0, `velocity: vec3<f32>` @16, `id: u32` @28, stride 32
+// (src/bin/particles.wgsl:1-12; produced on the CPU by encase at src/bin/main.rs:440-448).
+__global__ void __launch_bounds__(256) k_unpack_render(const float4 *__restrict__ pos, const float4 *__restrict__ vel,
+                                                       const uint32_t *__restrict__ slot_of,
+                                                       float4 *__restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = slot_of ? slot_of[i] : (uint32_t)i;
+    const float4 p = pos[s];
+    const float4 v = vel[s];
+    out[2 * i] = make_float4(p.x, p.y, p.z, 0.0f);
+    out[2 * i + 1] = make_float4(v.x, v.y, v.z, p.w);  // w = id bits at byte offset 28
+}
+
 // Forces in caller order (n*3 floats) for tests.
 __global__ void __launch_bounds__(256) k_unpack_forces(const float4 *__restrict__ frc,
                                                        const uint32_t *__restrict__ slot_of,

@@ -109,6 +109,12 @@ class Engine:
         _abi.check(self._lib.p3d_download_forces(self._h, out.ctypes.data, self._n))
         return out
 
+    def download_render(self, world_size: float) -> np.ndarray:
+        """The state as the reference app's render storage buffer (16-byte header + 32-byte particles)."""
+        out = np.zeros(16 + 32 * self._n, dtype=np.uint8)
+        _abi.check(self._lib.p3d_download_render(self._h, world_size, out.ctypes.data, out.nbytes, self._n))
+        return out
+
     def diagnostics(self) -> dict:
         d = (C.c_double * 8)()
         _abi.check(self._lib.p3d_diagnostics(self._h, d))

@@ -47,7 +47,7 @@ class Params(C.Structure):
 
 EXPORTS = [
     "p3d_abi_version", "p3d_create", "p3d_destroy", "p3d_last_error", "p3d_update", "p3d_upload", "p3d_step",
-    "p3d_download", "p3d_sync", "p3d_download_forces", "p3d_diagnostics", "p3d_set_option", "p3d_get_option",
+    "p3d_download", "p3d_sync", "p3d_download_forces", "p3d_download_render", "p3d_diagnostics", "p3d_set_option", "p3d_get_option",
     "p3d_get_timing", "p3d_get_counters", "p3d_set_stream", "p3d_device_buffer", "p3d_set_shard",
     "p3d_shard_range", "p3d_shard_force", "p3d_shard_integrate", "p3d_shard_commit",
     "p3d_ipc_export", "p3d_ipc_import", "p3d_ipc_close", "p3d_shard_integrate_fused",
@@ -87,6 +87,8 @@ def load():
     L.p3d_sync.argtypes = [vp]
     L.p3d_download_forces.restype = i32
     L.p3d_download_forces.argtypes = [vp, vp, sz]
+    L.p3d_download_render.restype = i32
+    L.p3d_download_render.argtypes = [vp, f32, vp, sz, sz]
     L.p3d_diagnostics.restype = i32
     L.p3d_diagnostics.argtypes = [vp, C.POINTER(C.c_double)]
     L.p3d_set_option.restype = i32

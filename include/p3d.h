@@ -78,6 +78,11 @@ int p3d_upload(p3d_engine *eng, const p3d_particle *in, size_t n, uint32_t id_co
 int p3d_step(p3d_engine *eng, const p3d_params *prm, float ts, int n_steps);
 int p3d_download(p3d_engine *eng, p3d_particle *out, size_t n);
 int p3d_sync(p3d_engine *eng);
+/* The resident state in the layout of the reference app's render storage buffer:
+ * WGSL `struct Particles { world_size: f32, length: u32, particles: array<Particle> }` with 32-byte particles
+ * (position vec3 @0, velocity vec3 @16, id u32 @28; src/bin/particles.wgsl:1-12).  Replaces the per-frame CPU
+ * serialisation by encase at src/bin/main.rs:440-448; `out` receives 16 + 32*n bytes ready for queue.write_buffer. */
+int p3d_download_render(p3d_engine *eng, float world_size, void *out, size_t out_bytes, size_t n);
 /* total_force of src/lib.rs:177-243 from the most recent step, in particle index order (n*3). */
 int p3d_download_forces(p3d_engine *eng, float *out_xyz, size_t n);
 /* out[0]=sum 0.5*|v|^2, out[1..3]=sum v, out[4]=max |v|^2, out[5]=count, out[6]=sum |p|^2, out[7]=0 */

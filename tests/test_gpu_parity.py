@@ -456,3 +456,26 @@ def test_fp32_microbenchmark_confirms_the_roofline_denominator():
     assert 0.90 <= out[0] / peak <= 1.02, out[0] / peak
     assert _abi.load().p3d_microbench(0, 0, 2000, out) == 0  # scalar FFMA: same datapath, a bit lower
     assert 0.80 <= out[0] / peak <= 1.02
+
+
+# ---------------------------------------------------------------- render-buffer interop
+@pytest.mark.parametrize("kernel", [_abi.FORCE_PAIR, _abi.FORCE_CELLS], ids=["typed_layout", "identity_layout"])
+def test_render_buffer_layout(default_params, kernel):
+    """p3d_download_render writes what encase writes for `GpuParticles` (src/bin/main.rs:89-96,440-448):
+    f32 world_size @0, u32 length @4, particles from byte 16 at a 32-byte stride (particles.wgsl:1-12)."""
+    e = p3.Engine(0)
+    e.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+    start = p3.generate_particles(10.0, 5000, seed=3)
+    start["vx"] = np.linspace(-1, 1, 5000, dtype=np.float32)
+    e.upload(start, 5)
+    e.step(p3.Engine.make_params(**default_params), TS, 2)
+    state = e.download()
+    buf = e.download_render(10.0)
+    e.close()
+    assert buf.nbytes == 16 + 32 * 5000
+    assert buf[:4].view("<f4")[0] == 10.0 and buf[4:8].view("<u4")[0] == 5000 and not buf[8:16].any()
+    rec = buf[16:].view(np.dtype([("p", "<f4", 3), ("pad0", "<u4"), ("v", "<f4", 3), ("id", "<u4")]))
+    assert rec.dtype.itemsize == 32
+    assert np.array_equal(rec["p"], np.stack([state["px"], state["py"], state["pz"]], 1))
+    assert np.array_equal(rec["v"], np.stack([state["vx"], state["vy"], state["vz"]], 1))
+    assert np.array_equal(rec["id"], state["id"]) and not rec["pad0"].any()
