@@ -91,7 +91,7 @@ struct p3d_engine {
     std::vector<int> seg_start_h, seg_end_h;
 
     DevBuf<float4> pos[2], vel, frc, spos;
-    DevBuf<uint32_t> perm, slot_of, sidx;
+    DevBuf<uint32_t> slot_of, sidx;
     DevBuf<uint8_t> seg_type, bclass;
     DevBuf<int> seg_start, seg_end, cnt;
     DevBuf<int2> cta_cnt, cta_off;
@@ -165,10 +165,8 @@ int canonicalise(const p3d_params *prm, DevParams &P) {
     P.inv_m = (m > 0.0f) ? 1.0f / m : std::numeric_limits<float>::infinity();
     if (m < 1.0f) {
         P.c2 = 2.0f / (1.0f - m);
-        P.kk = (1.0f + m) / (1.0f - m);
     } else {
         P.c2 = 0.0f;
-        P.kk = 2.0f;
     }
     P.rcut = (P.r < 1.0f) ? 1 : 0;
     P.reach = std::min(P.r, 1.0f);
@@ -181,7 +179,6 @@ int ensure_common(p3d_engine *e, size_t n, size_t ns) {
     if ((rc = e->pos[1].ensure(ns))) return rc;
     if ((rc = e->vel.ensure(ns))) return rc;
     if ((rc = e->frc.ensure(ns))) return rc;
-    if ((rc = e->perm.ensure(ns))) return rc;
     if ((rc = e->aos.ensure((n ? n : 1) * 7))) return rc;
     if ((rc = e->matrix.ensure(P3D_MAX_TYPES * P3D_MAX_TYPES))) return rc;
     if ((rc = e->flags.ensure(4))) return rc;
@@ -212,10 +209,6 @@ int build_layout_identity(p3d_engine *e, size_t n, uint32_t T) {
 
 int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T) {
     if (n > (size_t)0x7fff0000) return fail(P3D_ERR_INVALID, "n too large");
-    e->typed = true;
-    e->layout_version++;
-    e->B = e->B_next ? e->B_next : (n >= 65536 ? 256 : 128);
-    const int B = e->B;
     std::vector<size_t> count(T, 0);
     for (size_t i = 0; i < n; ++i) {
         const uint32_t id = in[i].id;
@@ -223,6 +216,10 @@ int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T) {
             return fail(P3D_ERR_BAD_ID, "particle %zu has id %u >= id_count %u (src/lib.rs:225-228)", i, id, T);
         ++count[id];
     }
+    e->typed = true;
+    e->layout_version++;
+    e->B = e->B_next ? e->B_next : (n >= 65536 ? 256 : 128);
+    const int B = e->B;
     e->seg_start_h.assign(T, 0);
     e->seg_end_h.assign(T, 0);
     size_t at = 0;
@@ -260,7 +257,6 @@ int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T) {
     if ((rc = e->sx.ensure(ns))) return rc;
     if ((rc = e->sy.ensure(ns))) return rc;
     if ((rc = e->sz.ensure(ns))) return rc;
-    if ((rc = e->perm.ensure(ns))) return rc;
     if ((rc = e->slot_of.ensure(n ? n : 1))) return rc;
     if ((rc = e->seg_type.ensure((size_t)e->M))) return rc;
     if ((rc = e->bclass.ensure((size_t)e->M))) return rc;
@@ -290,11 +286,11 @@ int launch_pack(p3d_engine *e, size_t n) {
     const int ns = e->n_slots;
     e->cur = 0;
     e->parity = 0;
-    k_fill_ghosts<<<(ns + 255) / 256, 256, 0, st>>>(e->pos[0].p, e->pos[1].p, e->vel.p, e->frc.p, e->perm.p, ns);
+    k_fill_ghosts<<<(ns + 255) / 256, 256, 0, st>>>(e->pos[0].p, e->pos[1].p, e->vel.p, e->frc.p, ns);
     e->counters[0]++;
     if (n) {
         k_pack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->aos.p, e->typed ? e->slot_of.p : nullptr, e->pos[0].p,
-                                                            e->vel.p, e->perm.p, (int)n, e->T, e->flags.p + 2);
+                                                            e->vel.p, (int)n, e->T, e->flags.p + 2);
         e->counters[0]++;
     }
     CU(cudaGetLastError());
@@ -754,7 +750,7 @@ void p3d_destroy(p3d_engine *e) {
     p3d_ipc_close(e);
     for (auto &b : e->pos) b.release();
     e->vel.release(); e->frc.release(); e->spos.release();
-    e->perm.release(); e->slot_of.release(); e->sidx.release();
+    e->slot_of.release(); e->sidx.release();
     e->seg_type.release(); e->bclass.release();
     e->seg_start.release(); e->seg_end.release(); e->cnt.release(); e->cta_cnt.release(); e->cta_off.release();
     for (auto &b : e->ckeys) b.release();

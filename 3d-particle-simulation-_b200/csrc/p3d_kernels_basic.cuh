@@ -10,10 +10,10 @@ struct AosParticle {
 };
 
 // ---------------------------------------------------------------------------------------------
-// K3a: fill every slot with a ghost (both position buffers), zero velocity/force, perm = ghost.
+// K3a: fill every slot with a ghost (both position buffers), zero velocity/force.
 __global__ void __launch_bounds__(256) k_fill_ghosts(float4 *__restrict__ pos0, float4 *__restrict__ pos1,
                                                      float4 *__restrict__ vel, float4 *__restrict__ frc,
-                                                     uint32_t *__restrict__ perm, int n_slots) {
+                                                     int n_slots) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slots) return;
     const float4 g = make_float4(P3D_GHOST_COORD, P3D_GHOST_COORD, P3D_GHOST_COORD, u2f(P3D_GHOST_ID));
@@ -21,7 +21,6 @@ __global__ void __launch_bounds__(256) k_fill_ghosts(float4 *__restrict__ pos0, 
     pos1[s] = g;
     vel[s] = make_float4(0.f, 0.f, 0.f, 0.f);
     frc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-    perm[s] = P3D_GHOST_ID;
 }
 
 // K3b: AoS (28 B, caller's index order) -> SoA float4 slots (type-sorted).  The block stages its
@@ -30,9 +29,8 @@ __global__ void __launch_bounds__(256) k_fill_ghosts(float4 *__restrict__ pos0, 
 // slot_of == nullptr: identity layout (slot = caller index); ids are then validated here
 // (err[0] |= 1 for an id >= id_count, the condition src/lib.rs:225-228 would index out of bounds on).
 __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, const uint32_t *__restrict__ slot_of,
-                                              float4 *__restrict__ pos, float4 *__restrict__ vel,
-                                              uint32_t *__restrict__ perm, int n, uint32_t id_count,
-                                              int *__restrict__ err) {
+                                              float4 *__restrict__ pos, float4 *__restrict__ vel, int n,
+                                              uint32_t id_count, int *__restrict__ err) {
     __shared__ float sm[256 * 7];
     const int base = blockIdx.x * 256;
     const int cnt = min(256, n - base);
@@ -46,7 +44,6 @@ __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, con
     if (f2u(p[6]) >= id_count) atomicOr(err, 1);
     pos[s] = make_float4(p[0], p[1], p[2], p[6]);  // w carries the id bits
     vel[s] = make_float4(p[3], p[4], p[5], 0.f);
-    perm[s] = (uint32_t)(base + t);
 }
 
 // K3c: SoA slots -> AoS in the caller's index order (src/lib.rs:268: index order preserved).
