@@ -25,8 +25,8 @@ struct DevParams {
     //   s(d) = f(d)/d = min(1/m - 1/d, 0) + a * max(0, min(c2 - c2*m/d, c2/d - c2))
     float inv_m;  // 1/m, or +inf when m <= 0 (the repulsion branch is then unreachable)
     float c2;     // 2/(1-m), or 0 when m >= 1 (the attraction branch is then unreachable)
-    int rcut;     // 1 when r < 1: the d2 < r^2 test cuts inside the force range and must be explicit
-    float reach;  // min(r, 1): beyond this distance the force is exactly zero
+    int rcut;     // 1 when r < max(1, m): the d2 < r^2 test cuts inside the force range and must be explicit
+    float reach;  // min(r, max(1, m)): beyond this distance the force is exactly zero
 };
 
 __device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }

@@ -168,8 +168,11 @@ int canonicalise(const p3d_params *prm, DevParams &P) {
     } else {
         P.c2 = 0.0f;
     }
-    P.rcut = (P.r < 1.0f) ? 1 : 0;
-    P.reach = std::min(P.r, 1.0f);
+    // The force law is non-zero on (0, 1) — and on (0, m) when m > 1, where the repulsion branch d < m
+    // (src/lib.rs:56-58) outlives the attraction branch.  The cutoff d < r (src/lib.rs:216-220) bites when r is smaller.
+    const float law_range = std::max(1.0f, m);
+    P.rcut = (P.r < law_range) ? 1 : 0;
+    P.reach = std::min(P.r, law_range);
     return P3D_OK;
 }
 

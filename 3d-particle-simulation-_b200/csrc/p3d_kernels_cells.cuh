@@ -2,7 +2,7 @@
 // analogue of the reference's spatial hash (src/lib.rs:135-236).
 //
 // The reference hashes cells of edge r into N buckets and scans 27 images x 27 cells.  Here the box
-// [-W/2, W/2]^3 is cut into nc^3 cells of edge W/nc >= reach = min(r, 1) — beyond `reach` the force
+// [-W/2, W/2]^3 is cut into nc^3 cells of edge W/nc >= reach = min(r, max(1, m)) — beyond `reach` the force
 // law of src/lib.rs:55-67 (and the cutoff of :216-220) is exactly zero — particles are sorted by
 // cell every step, and each particle scans the 27 neighbouring cells, periodic neighbours included.
 // Every in-range (particle, image) pair is visited exactly once ("ideal" physics: the reference's

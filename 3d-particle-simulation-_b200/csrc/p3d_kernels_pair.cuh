@@ -4,7 +4,7 @@
 // particle pairs.  Design:
 //   * Slots are grouped in blocks of B = 32*R particles of ONE type.  Every step a partition pass
 //     stages each type's particles as [interior ... ghosts ... boundary]; a block is INTERIOR when
-//     every member is farther than reach=min(r,1) from every face, so that only the offset-0 image
+//     every member is farther than reach = min(r, max(1, m)) from every face, so that only the offset-0 image
 //     of src/lib.rs:177-185 can be in range for any pair that involves it.
 //   * k_force_pair visits every unordered block pair {a,b} with at least one INTERIOR member once
 //     (circulant schedule: row a takes b = a+o, o = 0..M/2).  Inside a pair the relative position,
