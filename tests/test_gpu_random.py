@@ -76,3 +76,68 @@ def test_random_configuration_large(seed):
         e.set_option(_abi.OPT_FORCE_KERNEL, kernel)
         assert_parity(e.update(P, ts, parts), ideal, W, what=f"large seed {seed} kernel {kernel} {prm}")
     e.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_device_resident_session(seed):
+    """A device-resident session: parameters, world size, walls, kernel and step counts change between
+    p3d_step calls (as the reference UI does between frames, src/bin/main.rs:263-359); the oracle follows."""
+    rng = np.random.default_rng(9000 + seed)
+    prm, parts, _ = _case(200 + seed)
+    n = 2500
+    W = prm["world_size"]
+    T = prm["id_count"]
+    parts = p3.generate_particles(W, n, seed=seed, id_count=T)
+    parts["vy"] = rng.normal(0, 0.5, n).astype(np.float32)
+    e = p3.Engine(0)
+    e.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_PAIR)  # type-grouped layout: every kernel can run on it
+    e.upload(parts, T)
+    ref = parts
+    ts = float(np.float32(1 / 60))
+    for it in range(6):
+        if rng.integers(0, 2):
+            prm["walls"] = not prm["walls"]
+        if rng.integers(0, 2):  # the UI keeps world_size >= 2r (main.rs:286-290); shrinking can leave particles outside
+            prm["world_size"] = float(max(2 * prm["particle_effect_radius"], W * rng.uniform(0.8, 1.3)))
+        prm["min_pull_ratio"] = float(rng.uniform(0, 1))
+        prm["attraction_matrix"] = [float(x) for x in rng.uniform(-1, 1, T * T)]
+        e.set_option(_abi.OPT_FORCE_KERNEL, int(rng.choice([_abi.FORCE_REFERENCE_ORDER, _abi.FORCE_PAIR, _abi.FORCE_CELLS])))
+        steps = int(rng.choice([1, 2, 7]))
+        e.step(p3.Engine.make_params(**prm), ts, steps)
+        for _ in range(steps):
+            ref = O.update(prm, ts, ref, mode=O.IDEAL)["out"]
+        out = e.download()
+        # several steps of independent f32 rounding: 1e-5 per step
+        assert_parity(out, ref, prm["world_size"], tol=1e-5 * max(1, steps) * 2, what=f"session {seed} iteration {it} {prm}")
+        ref = out  # continue from the GPU state so that rounding does not accumulate across iterations
+    e.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_sharding_emulated(seed):
+    """Random world sizes / kernels / parameters: the ranks' partial forces must sum to the full force and the
+    ranks' integrate ranges must tile the slots (all ranks run in turn on one device; none waits on another)."""
+    rng = np.random.default_rng(7000 + seed)
+    prm, _, ts = _case(300 + seed)
+    T, W = prm["id_count"], prm["world_size"]
+    n = int(rng.choice([900, 5000, 12000]))
+    parts = p3.generate_particles(W, n, seed=seed, id_count=T)
+    world = int(rng.choice([2, 3, 5, 8]))
+    kernel = int(rng.choice([_abi.FORCE_REFERENCE_ORDER, _abi.FORCE_PAIR, _abi.FORCE_CELLS]))
+    ref = O.update(prm, ts, parts, mode=O.IDEAL, want_force=True)
+    P = p3.Engine.make_params(**prm)
+    e = p3.Engine(0)
+    e.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+    e.set_shard(0, world)
+    e.upload(parts, T)
+    total = np.zeros((n, 3))
+    for r in range(world):
+        e.set_shard(r, world)
+        e.shard_force(P)
+        e.sync()
+        total += e.download_forces()
+    f = ref["force"].astype(np.float64)
+    frms = max(np.sqrt((f ** 2).sum(1).mean()), 1e-30)
+    err = np.linalg.norm(total - f, axis=1) / np.maximum(np.linalg.norm(f, axis=1), frms)
+    assert err.max() < 1e-5, f"world {world} kernel {kernel} {prm}"
+    e.close()
