@@ -92,3 +92,25 @@ def test_integrate_only_matches_update(g1, default_params):
     r = O.update(default_params, TS, g1["start"], mode=O.IDEAL, want_force=True)
     again = O.integrate(default_params, TS, g1["start"], r["force"])
     assert again.tobytes() == r["out"].tobytes()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_cell_walk_equals_bruteforce_on_random_configurations(seed):
+    """The restated spatial-hash walk (lib.rs:135-236, each bucket once) against the independent O(27 N^2) f64
+    scan, over random parameters incl. r < 1, m > 1, W == 2r, many types and positions outside the box."""
+    rng = np.random.default_rng(400 + seed)
+    T = int(rng.integers(1, 7))
+    W = float(rng.uniform(4.0, 30.0))
+    r = float(rng.choice([rng.uniform(0.2, 1.0), rng.uniform(1.0, min(W / 2, 5.0)), W / 2]))
+    prm = dict(world_size=W, coefficient=0.5, interaction_force=1.0, min_pull_ratio=float(rng.choice([0.0, 0.3, 1.0, 1.2])),
+               particle_effect_radius=r, id_count=T, attraction_matrix=[float(x) for x in rng.uniform(-1.5, 1.5, T * T)])
+    n = int(rng.choice([3, 50, 400, 900]))
+    p = np.zeros(n, O.PARTICLE)
+    spread = W / 2 * (1.4 if seed % 4 == 0 else 1.0)
+    for k in ("px", "py", "pz"):
+        p[k] = rng.uniform(-spread, spread, n).astype(np.float32)
+    p["id"] = rng.integers(0, T, n)
+    f = O.update(prm, TS, p, mode=O.IDEAL, want_force=True)["force"].astype(np.float64)
+    bf = O.bruteforce_forces(prm, p)
+    scale = max(np.abs(bf).max(), 1.0)
+    assert np.abs(f - bf).max() / scale < 5e-6
