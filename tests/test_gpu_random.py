@@ -141,3 +141,20 @@ def test_random_sharding_emulated(seed):
     err = np.linalg.norm(total - f, axis=1) / np.maximum(np.linalg.norm(f, axis=1), frms)
     assert err.max() < 1e-5, f"world {world} kernel {kernel} {prm}"
     e.close()
+
+
+@pytest.mark.parametrize("n", [3, 31, 32, 33, 127, 128, 129, 255, 256, 257, 511, 512, 513, 4095, 4096, 4097, 65535, 65536, 65537])
+def test_sizes_around_block_boundaries(n, default_params):
+    """Particle counts straddling every granularity in the engine: warp (32), block (128/256), the AUTO
+    thresholds (512), the 256-block switch (65,536)."""
+    W = max(6.0, round(float(n) ** (1 / 3), 1))
+    prm = dict(default_params, world_size=W)
+    parts = p3.generate_particles(W, n, seed=n)
+    ideal = O.update(prm, 1 / 60, parts, mode=O.IDEAL)["out"]
+    e = p3.Engine(0)
+    P = p3.Engine.make_params(**prm)
+    kernels = [_abi.FORCE_AUTO, _abi.FORCE_PAIR, _abi.FORCE_CELLS] + ([_abi.FORCE_REFERENCE_ORDER] if n <= 4097 else [])
+    for kernel in kernels:
+        e.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+        assert_parity(e.update(P, 1 / 60, parts), ideal, W, what=f"n={n} kernel={kernel}")
+    e.close()
