@@ -428,26 +428,18 @@ int launch_force(p3d_engine *e, const DevParams &P) {
             const int i0 = std::min(ns, e->rank * per), i1 = std::min(ns, i0 + per);
             if (i1 > i0) {
                 const size_t sm = (size_t)P.T * P.T * sizeof(float);
-                if (P.rcut)
-                    k_force_cells<true><<<(i1 - i0 + kCellThreads - 1) / kCellThreads, kCellThreads, sm, st>>>(
-                        e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_off.p, ns, i0, i1, g, e->frc.p, P, e->matrix.p,
-                        flag_cur);
-                else
-                    k_force_cells<false><<<(i1 - i0 + kCellThreads - 1) / kCellThreads, kCellThreads, sm, st>>>(
-                        e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_off.p, ns, i0, i1, g, e->frc.p, P, e->matrix.p,
-                        flag_cur);
-                e->counters[0]++;
+                const unsigned cg = (unsigned)((i1 - i0 + kCellThreads - 1) / kCellThreads);
+#define P3D_CELL_ARGS e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_off.p, ns, i0, i1, g, e->frc.p, P, e->matrix.p, flag_cur
+                // in-box positions (flag clear): the image follows from the neighbour cell ...
+                if (P.rcut) k_force_cells<true, false><<<cg, kCellThreads, sm, st>>>(P3D_CELL_ARGS);
+                else        k_force_cells<false, false><<<cg, kCellThreads, sm, st>>>(P3D_CELL_ARGS);
+                // ... some particle outside the box (flag set): nearest of the reference's three images per axis
+                k_force_cells<true, true><<<cg, kCellThreads, sm, st>>>(P3D_CELL_ARGS);
+#undef P3D_CELL_ARGS
+                e->counters[0] += 2;
                 e->counters[1]++;
             }
             if (e->step_ev) CU(cudaEventRecord(e->step_ev[2], st));
-            // out-of-box inputs (flag set): the reference-order kernel takes the whole step instead
-            const int perb = ((e->M + e->world - 1) / e->world) * e->B;
-            const int r0 = std::min(ns, e->rank * perb), r1 = std::min(ns, r0 + perb);
-            if (r1 > r0) {
-                k_force_ref<kRefTile><<<(r1 - r0 + kRefTile - 1) / kRefTile, kRefTile, ref_smem(kRefTile, P.T), st>>>(
-                    pos, ns, r0, r1, e->frc.p, P, e->matrix.p, flag_cur, 1);
-                e->counters[0]++;
-            }
             CU(cudaGetLastError());
             if (e->opt_faithful) return launch_quirk(e, P, g, flag_cur);
             return P3D_OK;

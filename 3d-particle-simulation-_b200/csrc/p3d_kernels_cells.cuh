@@ -22,9 +22,17 @@ struct CellGrid {
     float half;     // W / 2
 };
 
+// Cell of a coordinate, taken modulo the box: positions outside [-W/2, W/2) (callers may pass anything, and a
+// fast particle can leave the box, src/lib.rs:74-92 wraps only once) land in the cell of their periodic
+// image, so that every pair the reference can reach through its offsets -W, 0, +W sits in adjacent cells.
 __device__ __forceinline__ int cell_axis(float x, const CellGrid g) {
-    int c = (int)floorf((x + g.half) * g.inv_cs);
-    return min(max(c, 0), g.nc - 1);  // x == +W/2 lands in the last cell
+    const float W = 2.0f * g.half;
+    float u = x + g.half;
+    // in-box positions (x == +W/2 included: walls clamp particles exactly there) keep their own cell, so that
+    // the image of a neighbour follows from the neighbour cell; only outside positions are wrapped
+    if (!(u >= 0.0f && u <= W)) u = u - W * floorf(u / W);
+    int c = (int)floorf(u * g.inv_cs);
+    return min(max(c, 0), g.nc - 1);  // x == +W/2 lands in the last cell; NaN lands in cell 0
 }
 
 // keys[s] = linear cell index of slot s (ghosts: nc^3, sorted to the end); vals[s] = s.
@@ -64,16 +72,28 @@ __global__ void __launch_bounds__(256) k_cell_gather(const float4 *__restrict__ 
 
 // One candidate of the cell list: the reference's relative position (src/lib.rs:211-212) and the
 // branch-free force law of k_force_pair.
-template <bool RCUT>
-__device__ __forceinline__ void cell_pair(const float4 q, float px, float py, float pz, const float *arow, float c2,
+// GENERAL (some particle is outside the box): the image is not implied by the neighbour cell any more, so
+// each axis takes the nearest of the reference's three candidates `other - (position + offset)`,
+// offset in {-W, 0, +W} (src/lib.rs:190-192,211-212) — pairs that would need a larger offset are not
+// reachable in the reference either and fail the distance test here too.
+template <bool RCUT, bool GENERAL>
+__device__ __forceinline__ void cell_pair(const float4 q, float px, float py, float pz, const float *sx3,
+                                          const float *sy3, const float *sz3, const float *arow, float c2,
                                           float ncm, float nc2, float im, float r2, float &ax, float &ay, float &az) {
-    const float rx = __fsub_rn(q.x, px), ry = __fsub_rn(q.y, py), rz = __fsub_rn(q.z, pz);
+    float rx, ry, rz;
+    if (GENERAL) {
+        rx = nearest_image3(q.x, sx3[0], sx3[2], sx3[1]);
+        ry = nearest_image3(q.y, sy3[0], sy3[2], sy3[1]);
+        rz = nearest_image3(q.z, sz3[0], sz3[2], sz3[1]);
+    } else {
+        rx = __fsub_rn(q.x, px); ry = __fsub_rn(q.y, py); rz = __fsub_rn(q.z, pz);
+    }
     const float d2 = fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, 1.0e-30f)));
     const float inv = rsqrt_approx(d2);
     const float p1 = fmaf(inv, ncm, c2), p2 = fmaf(inv, c2, nc2);
     float ti = fmaxf(fminf(p1, p2), 0.0f);
     float rs = fminf(im - inv, 0.0f);
-    if (RCUT) {
+    if (RCUT || GENERAL) {  // (in GENERAL mode a candidate may be a far image: the cutoff must be explicit)
         if (!(d2 < r2)) { ti = 0.0f; rs = 0.0f; }
     }
     const float s = fmaf(arow[f2u(q.w)], ti, rs);
@@ -92,7 +112,7 @@ __device__ __forceinline__ void cell_pair(const float4 q, float px, float py, fl
 constexpr int kCellThreads = 128;
 constexpr int kCellRuns = 18;
 
-template <bool RCUT>
+template <bool RCUT, bool GENERAL>
 __global__ void __launch_bounds__(kCellThreads) k_force_cells(const float4 *__restrict__ cpos,
                                                               const uint32_t *__restrict__ keys_sorted,
                                                               const uint32_t *__restrict__ vals_sorted,
@@ -101,7 +121,7 @@ __global__ void __launch_bounds__(kCellThreads) k_force_cells(const float4 *__re
                                                               float4 *__restrict__ frc, DevParams P,
                                                               const float *__restrict__ matrix,
                                                               const int *__restrict__ flags) {
-    if (flags[0] != 0) return;  // out-of-box input: the reference-order kernel takes the step
+    if ((flags[0] != 0) != GENERAL) return;  // the in-box and the general variant are both launched; one runs
     extern __shared__ float smat_dyn[];
     __shared__ uint32_t run_lo[kCellRuns][kCellThreads], run_hi[kCellRuns][kCellThreads];
     __shared__ uint8_t run_img[kCellRuns][kCellThreads];  // 2 bits per axis: 0 = offset 0, 1 = +W, 2 = -W
@@ -171,11 +191,12 @@ __global__ void __launch_bounds__(kCellThreads) k_force_cells(const float4 *__re
 #pragma unroll
             for (int u = 0; u < 4; ++u) q[u] = __ldg(cpos + j + u);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) cell_pair<RCUT>(q[u], px, py, pz, arow, c2, ncm, nc2, im, r2, ax, ay, az);
+            for (int u = 0; u < 4; ++u)
+                cell_pair<RCUT, GENERAL>(q[u], px, py, pz, sx3, sy3, sz3, arow, c2, ncm, nc2, im, r2, ax, ay, az);
             j += 4;
             continue;
         }
-        cell_pair<RCUT>(__ldg(cpos + j), px, py, pz, arow, c2, ncm, nc2, im, r2, ax, ay, az);
+        cell_pair<RCUT, GENERAL>(__ldg(cpos + j), px, py, pz, sx3, sy3, sz3, arow, c2, ncm, nc2, im, r2, ax, ay, az);
         ++j;
     }
 done:

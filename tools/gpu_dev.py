@@ -153,6 +153,14 @@ if __name__ == "__main__":
         parity(16384, 25.4, _abi.FORCE_PAIR, walls=True, acceleration=(0.0, -1.0, 0.0))
         parity(16384, 25.4, _abi.FORCE_PAIR, particle_effect_radius=0.8)
         parity(20000, 64.0, _abi.FORCE_PAIR, plummer=True)
+    if "oob" in what:  # one particle outside the box: the general cell-list variant instead of an O(N^2) fallback
+        prm = p3.default_params_dict(); prm["world_size"] = 101.6
+        parts = p3.generate_particles(101.6, 1048576, 42); parts["px"][7] += 101.6
+        eng = p3.Engine(0); eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_CELLS); eng.set_option(_abi.OPT_TIMING, 1)
+        P = p3.Engine.make_params(**prm); eng.upload(parts, 5); eng.step(P, 0.0, 1); eng.sync(); eng.step(P, 0.0, 5); t = eng.timing()
+        print(f"oob n=1048576 cells-general: force {t['force']/5:.3f} ms/step", flush=True)
+        ref = O.update(prm, 0.0, parts, mode=O.IDEAL, want_force=True)["force"]
+        f = eng.download_forces(); print("oob max |dF|", np.abs(f - ref).max(), flush=True); eng.close()
     if "graph" in what:
         for n, W in ((1000, 10.0), (16384, 25.4), (262144, 64.0), (1048576, 101.6)):
             for kernel in (_abi.FORCE_CELLS, _abi.FORCE_REFERENCE_ORDER) if n == 1000 else (_abi.FORCE_CELLS,):
