@@ -102,3 +102,16 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", ".rs", ".toml", "Makefile")):
                 text = open(os.path.join(dp, f), errors="replace").read()
                 assert "p3d_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/p3d.h must be consumable from C (cgo / bindgen / ctypes generators): C99, no C++ or torch types."""
+    import subprocess
+
+    src = tmp_path / "h.c"
+    src.write_text('#include "p3d.h"\nint main(void) { p3d_params p; (void)p; return sizeof(p3d_particle) == 28 ? 0 : 1; }\n')
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-L", os.path.join(ROOT, "3d-particle-simulation-_b200"), "-o", str(tmp_path / "h"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(tmp_path / "h")]).returncode == 0
