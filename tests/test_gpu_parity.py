@@ -479,3 +479,19 @@ def test_render_buffer_layout(default_params, kernel):
     assert np.array_equal(rec["p"], np.stack([state["px"], state["py"], state["pz"]], 1))
     assert np.array_equal(rec["v"], np.stack([state["vx"], state["vy"], state["vz"]], 1))
     assert np.array_equal(rec["id"], state["id"]) and not rec["pad0"].any()
+
+
+# ---------------------------------------------------------------- the ABI from plain C
+def test_c_consumer_of_the_abi(tmp_path):
+    """tests/c/abi_smoke.c links libp3d.so from C99 and drives update / upload / step / download / render."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "3d-particle-simulation-_b200")
+    exe = tmp_path / "abi_smoke"
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-O1", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                        os.path.join(root, "tests", "c", "abi_smoke.c"), "-L", pkg, "-lp3d", f"-Wl,-rpath,{pkg}", "-lm",
+                        "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
