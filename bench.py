@@ -410,6 +410,37 @@ def run_engine(args):
         }
         eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_PAIR)
 
+    # ---------------- the other BASELINE.json configs, for the record (parity-test cases, not bench lines) ----------------
+    if world == 1 and rank == 0 and not args.no_cells:
+        extras = {}
+        for tag, n_x, W_x, plummer in (("config1_default_scene_n1000", 1000, 10.0, False),
+                                       ("config2_uniform_n16384", 16384, 25.4, False),
+                                       ("config3_plummer_n262144", 262144, 64.0, True)):
+            prm_x = dict(prm, world_size=W_x)
+            P_x = p3.Engine.make_params(**prm_x)
+            parts_x = p3.generate_plummer(W_x, n_x, W_x / 6, seed=SEED) if plummer else p3.generate_particles(W_x, n_x, seed=SEED)
+            row = {"n_particles": n_x, "world_size": W_x, "cloud": "plummer a=W/6" if plummer else "uniform"}
+            for name, kernel in (("all_pairs", _abi.FORCE_PAIR if n_x >= 4096 else _abi.FORCE_REFERENCE_ORDER), ("cell_list", _abi.FORCE_CELLS)):
+                ex = p3.Engine(local)
+                ex.set_stream(stream.cuda_stream)
+                ex.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+                ex.upload(parts_x, prm["id_count"])
+                ex.step(P_x, TS, 6)
+                ex.sync()
+                reps = 20 if n_x <= 16384 or name == "cell_list" else 6
+                x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                x0.record(stream)
+                ex.step(P_x, TS, reps)
+                x1.record(stream)
+                torch.cuda.synchronize()
+                ms_x = x0.elapsed_time(x1) / reps
+                row[name] = {"ms_per_step": ms_x, "steps_per_s": 1e3 / ms_x}
+                if name == "all_pairs":
+                    row[name]["interactions_per_s"] = float(n_x) * n_x / (ms_x * 1e-3)
+                ex.close()
+            extras[tag] = row
+        line["other_configs"] = extras
+
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     if world == 1 and rank == 0 and not args.no_cpu:
         r = cpu_reference_sample(prm, parts, args.cpu_seconds)
