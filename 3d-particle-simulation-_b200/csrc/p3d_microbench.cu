@@ -267,10 +267,67 @@ __global__ void __launch_bounds__(32, 16) mb_pack(float *out, int iters, float a
     if (acc == 123.456f) out[0] = acc;
 }
 
+// Two-phase variant of mb_pack: phase 1 computes d and both scalars for G i-particles, phase 2 issues the 6*G
+// accumulations back to back in an order where consecutive FFMA2 share one source register pair.
+template <int G, bool FULL>
+__global__ void __launch_bounds__(32, 16) mb_pack2(float *out, int iters, float a, float b) {
+    constexpr int R = 8;
+    float nix[R], niy[R], niz[R];
+    float2 aix[R], aiy[R], aiz[R];
+    float2 jx = make_float2(a + threadIdx.x, a - threadIdx.x), jy = make_float2(b + threadIdx.x, 2.f * b), jz = make_float2(a, b);
+    float2 ajx = make_float2(0.f, 0.f), ajy = ajx, ajz = ajx;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        nix[r] = a * (r + 1) + threadIdx.x; niy[r] = b * (r + 2); niz[r] = a + b * r;
+        aix[r] = aiy[r] = aiz[r] = make_float2(0.f, 0.f);
+    }
+    const float2 c2 = make_float2(a * 2.8f, a * 2.8f), nc2 = make_float2(-a, -a), im = make_float2(3.3f * a, 3.3f * a),
+                 nim = make_float2(-3.3f * a, -3.3f * a), neg1 = make_float2(-1.f, -1.f), tiny = make_float2(1e-30f, 1e-30f);
+    const float2 aij = make_float2(out[1], out[1]), aji = make_float2(out[2], out[2]);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int g0 = 0; g0 < R; g0 += G) {
+            float2 dx[G], dy[G], dz[G], sij[G], sji[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int r = g0 + g;
+                dx[g] = __fadd2_rn(jx, make_float2(nix[r], nix[r]));
+                dy[g] = __fadd2_rn(jy, make_float2(niy[r], niy[r]));
+                dz[g] = __fadd2_rn(jz, make_float2(niz[r], niz[r]));
+                float2 d2 = __ffma2_rn(dx[g], dx[g], tiny);
+                d2 = __ffma2_rn(dy[g], dy[g], d2);
+                d2 = __ffma2_rn(dz[g], dz[g], d2);
+                const float2 inv = FULL ? make_float2(rsq(d2.x), rsq(d2.y)) : d2;
+                float2 rs = __ffma2_rn(inv, neg1, im);
+                const float2 p2 = __ffma2_rn(inv, im, nim);
+                float2 ti = FULL ? make_float2(fmaxf(fminf(rs.x, p2.x), 0.f), fmaxf(fminf(rs.y, p2.y), 0.f)) : __fadd2_rn(rs, p2);
+                if (FULL) rs = make_float2(fminf(rs.x, 0.f), fminf(rs.y, 0.f));
+                sij[g] = __ffma2_rn(aij, ti, rs);
+                sji[g] = __ffma2_rn(aji, ti, rs);
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int r = g0 + g;
+                aix[r] = __ffma2_rn(dx[g], sij[g], aix[r]);
+                ajx = __ffma2_rn(dx[g], sji[g], ajx);
+                ajy = __ffma2_rn(dy[g], sji[g], ajy);
+                aiy[r] = __ffma2_rn(dy[g], sij[g], aiy[r]);
+                aiz[r] = __ffma2_rn(dz[g], sij[g], aiz[r]);
+                ajz = __ffma2_rn(dz[g], sji[g], ajz);
+            }
+        }
+        jx.x += 1e-3f;
+    }
+    float acc = ajx.x + ajx.y + ajy.x + ajy.y + ajz.x + ajz.y;
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc += aix[r].x + aix[r].y + aiy[r].x + aiy[r].y + aiz[r].x + aiz[r].y;
+    if (acc == 123.456f) out[0] = acc;
+}
+
 }  // namespace
 
 extern "C" int p3d_microbench(int device, int kind, int iters, double out[4]) {
-    if (!out || iters <= 0 || kind < 0 || kind > 17 + 64) return P3D_ERR_INVALID;
+    if (!out || iters <= 0 || kind < 0 || kind > 100) return P3D_ERR_INVALID;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
         cudaGetLastError();
@@ -330,6 +387,12 @@ extern "C" int p3d_microbench(int device, int kind, int iters, double out[4]) {
         if (kind == 18 + 19) mb_pack<19><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
         if (kind == 18 + 35) mb_pack<35><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
         if (kind == 18 + 32) mb_pack<32><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 90) mb_pack2<2, false><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 91) mb_pack2<4, false><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 92) mb_pack2<8, false><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 93) mb_pack2<2, true><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 94) mb_pack2<4, true><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+        if (kind == 95) mb_pack2<8, true><<<grid, threads>>>(d, iters, 0.999f, 0.001f);
         if (kind == 12) mb_generic<17, 0, 0, 0, 0><<<grid, threads>>>(d, iters, 0.999f, 0.001f);  // FFMA2 only
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return P3D_ERR_CUDA; }

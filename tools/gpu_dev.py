@@ -136,6 +136,14 @@ def micro4():
 
 if __name__ == "__main__":
     what = sys.argv[1:] or ["parity", "timing", "micro"]
+    if "micro5" in what:
+        L = _abi.load()
+        for kind, name in ((90, "two-phase G=2, F2 only (16 F2)"), (91, "two-phase G=4, F2 only"), (92, "two-phase G=8, F2 only"),
+                           (93, "two-phase G=2, full body"), (94, "two-phase G=4, full body"), (95, "two-phase G=8, full body")):
+            out = (C.c_double * 4)()
+            rc = L.p3d_microbench(0, kind, 4000, out)
+            cyc = out[3] * 1e6 * out[2] * 4 / (out[0] / 32)
+            print(f"micro5 [{name:34s}] rc={rc} -> {cyc:6.2f} SMSP-cycles per pair-pack", flush=True)
     if "micro4" in what:
         micro4()
     if "micro3" in what:
