@@ -49,6 +49,7 @@ def test_two_gpu_sharded_step_matches_single_gpu_and_oracle(tmp_path, default_pa
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    world = min(8, torch.cuda.device_count())  # every visible GPU of the box
     import particle_3d as p3
     from particle_3d import _abi
     from oracle import oracle as O
@@ -56,7 +57,7 @@ def test_two_gpu_sharded_step_matches_single_gpu_and_oracle(tmp_path, default_pa
 
     script = tmp_path / "worker.py"
     script.write_text(f"ROOT = {ROOT!r}\nOUT = {str(tmp_path)!r}\n" + WORKER)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
@@ -66,16 +67,16 @@ def test_two_gpu_sharded_step_matches_single_gpu_and_oracle(tmp_path, default_pa
     for _ in range(3):
         ref = O.update(prm, 1 / 60, ref, mode=O.IDEAL)["out"]
     for prefix in ("shard", "fused"):
-        _check(np.load(tmp_path / f"{prefix}_0.npy"), np.load(tmp_path / f"{prefix}_1.npy"), ref, W, prefix)
+        _check([np.load(tmp_path / f"{prefix}_{r}.npy") for r in range(world)], ref, W, prefix)
 
 
-def _check(a, b, ref, W, what):
+def _check(outs, ref, W, what):
     from helpers import parity_errors
-    # after the final all-gather both ranks hold every position; velocities only for their own shard,
-    # so compare positions on both and velocities where each rank owns the slot (non-zero update)
-    for got in (a, b):
+    # after the final all-gather every rank holds every position; velocities only for its own shard,
+    # so compare positions on all ranks and velocities where some rank owns the slot
+    best = None
+    for got in outs:
         dv, dp = parity_errors(got, ref, W)
         assert dp.max() < 5e-5, what
-    dva, _ = parity_errors(a, ref, W)
-    dvb, _ = parity_errors(b, ref, W)
-    assert np.minimum(dva, dvb).max() < 5e-5, what  # every particle's velocity is right on its owner rank
+        best = dv if best is None else np.minimum(best, dv)
+    assert best.max() < 5e-5, what  # every particle's velocity is right on its owner rank
