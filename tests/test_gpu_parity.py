@@ -495,3 +495,35 @@ def test_c_consumer_of_the_abi(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+# ---------------------------------------------------------------- options / timing surface
+def test_options_round_trip_and_timing(default_params):
+    e = p3.Engine(0)
+    for opt, val in ((_abi.OPT_FORCE_KERNEL, _abi.FORCE_CELLS), (_abi.OPT_TIMING, 1), (_abi.OPT_GRAPH, 0),
+                     (_abi.OPT_BLOCK_SORT, 0), (_abi.OPT_BLOCK_SIZE, 256), (_abi.OPT_FAITHFUL, 1)):
+        e.set_option(opt, val)
+        assert e.get_option(opt) == val
+    for bad in ((_abi.OPT_FORCE_KERNEL, 9), (_abi.OPT_BLOCK_SIZE, 100), (77, 1)):
+        with pytest.raises(p3.P3DError):
+            e.set_option(*bad)
+    e.set_option(_abi.OPT_FAITHFUL, 0)
+    e.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_PAIR)
+    W = 20.0
+    prm = dict(default_params, world_size=W)
+    start = p3.generate_particles(W, 8000, seed=2)
+    e.upload(start, 5)
+    e.step(p3.Engine.make_params(**prm), TS, 3)
+    t = e.timing()
+    assert t["steps"] == 3 and t["force"] > 0 and t["integrate"] > 0 and t["pair"] > 0
+    assert abs(t["total"] - (t["force"] + t["integrate"])) < 1e-3
+    # block sort off: every block is treated as a boundary block (exact image arithmetic everywhere), same results
+    out = e.download()
+    ref = start
+    for _ in range(3):
+        ref = O.update(prm, TS, ref, mode=O.IDEAL)["out"]
+    dv, dp = parity_errors(out, ref, W)
+    assert dv.max() < 5e-5 and dp.max() < 5e-5
+    with pytest.raises(p3.P3DError):  # id_count must match the uploaded layout
+        e.step(p3.Engine.make_params(**dict(prm, id_count=4, attraction_matrix=[0.0] * 16)), TS, 1)
+    e.close()
