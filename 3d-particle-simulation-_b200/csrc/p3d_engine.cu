@@ -47,7 +47,8 @@ int fail(int code, const char *fmt, ...) {
 constexpr int kMaxTimedSteps = 512;
 constexpr int kEv = 5;  // events per timed step
 constexpr int kRefTile = 128;       // threads per CTA of the reference-order kernel
-constexpr int kCellsAutoMin = 512;  // P3D_FORCE_AUTO uses the cell list from this n, the reference-order kernel below
+constexpr int kCellsAutoMin = 192;  // P3D_FORCE_AUTO uses the cell list from this n (its ~12 launches cost ~35 us),
+                                    // the single-launch reference-order kernel below
 
 template <typename T>
 struct DevBuf {

@@ -101,7 +101,7 @@ enum p3d_option {
     P3D_OPT_BLOCK_SIZE = 4    /* particles per block of the pair kernel: 0 = auto (256 from 65,536 particles, else 128), 128 (R=4) or 256 (R=8); applies at the next upload */
 };
 enum p3d_force_kernel {
-    P3D_FORCE_AUTO = 0,      /* CELLS for n >= 512 (all-pairs when the box is narrower than three cells), else REFERENCE_ORDER */
+    P3D_FORCE_AUTO = 0,      /* CELLS for n >= 192 (all-pairs when the box is narrower than three cells), else REFERENCE_ORDER */
     P3D_FORCE_REFERENCE_ORDER = 1, /* one thread per particle, exact sqrt/div, all three images per axis */
     P3D_FORCE_PAIR = 2,      /* symmetric block-pair kernel, packed FP32x2, rsqrt (all N^2 pairs) */
     P3D_FORCE_CELLS = 3      /* uniform-grid cell list: the GPU analogue of the reference's spatial hash

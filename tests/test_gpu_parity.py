@@ -275,7 +275,7 @@ def test_particles_run_equals_repeated_update(default_params):
 def test_auto_kernel_selection_and_counters(eng, default_params):
     eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_AUTO)
     c0 = eng.counters()
-    eng.update(p3.Engine.make_params(**default_params), TS, p3.generate_particles(10.0, 300, seed=1))
+    eng.update(p3.Engine.make_params(**default_params), TS, p3.generate_particles(10.0, 150, seed=1))
     c1 = eng.counters()
     assert c1["force"] - c0["force"] == 1 and c1["integrate"] - c0["integrate"] == 1  # reference-order kernel
     prm = dict(default_params, world_size=20.0)

@@ -143,10 +143,10 @@ def test_random_sharding_emulated(seed):
     e.close()
 
 
-@pytest.mark.parametrize("n", [3, 31, 32, 33, 127, 128, 129, 255, 256, 257, 511, 512, 513, 4095, 4096, 4097, 65535, 65536, 65537])
+@pytest.mark.parametrize("n", [3, 31, 32, 33, 127, 128, 129, 191, 192, 193, 255, 256, 257, 511, 512, 513, 4095, 4096, 4097, 65535, 65536, 65537])
 def test_sizes_around_block_boundaries(n, default_params):
     """Particle counts straddling every granularity in the engine: warp (32), block (128/256), the AUTO
-    thresholds (512), the 256-block switch (65,536)."""
+    threshold (192), the 256-block switch (65,536)."""
     W = max(6.0, round(float(n) ** (1 / 3), 1))
     prm = dict(default_params, world_size=W)
     parts = p3.generate_particles(W, n, seed=n)
