@@ -129,6 +129,7 @@ struct p3d_engine {
     void *peer_ptr[8][3] = {};
     bool peer_open[8] = {};
     bool peers_ready = false;
+    bool ipc_exported = false;  // frc/pos were handed to peers: they must not be reallocated until p3d_ipc_close
 
     // timing
     std::vector<cudaEvent_t> ev;  // kEv per timed step: start, after partition, after pair, after force, after integrate
@@ -179,6 +180,9 @@ int canonicalise(const p3d_params *prm, DevParams &P) {
 
 int ensure_common(p3d_engine *e, size_t n, size_t ns) {
     int rc;
+    if (e->ipc_exported && ((size_t)ns > e->pos[0].cap || (size_t)ns > e->pos[1].cap || (size_t)ns > e->frc.cap))
+        return fail(P3D_ERR_INVALID, "upload needs %zu slots but the position/force buffers are exported to peer GPUs "
+                    "(p3d_ipc_export); call p3d_ipc_close on every rank, upload, then export/import again", (size_t)ns);
     if ((rc = e->pos[0].ensure(ns))) return rc;
     if ((rc = e->pos[1].ensure(ns))) return rc;
     if ((rc = e->vel.ensure(ns))) return rc;
@@ -252,6 +256,9 @@ int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T) {
 
     const size_t ns = (size_t)e->n_slots;
     int rc;
+    if (e->ipc_exported && ((size_t)ns > e->pos[0].cap || (size_t)ns > e->pos[1].cap || (size_t)ns > e->frc.cap))
+        return fail(P3D_ERR_INVALID, "upload needs %zu slots but the position/force buffers are exported to peer GPUs "
+                    "(p3d_ipc_export); call p3d_ipc_close on every rank, upload, then export/import again", (size_t)ns);
     if ((rc = e->pos[0].ensure(ns))) return rc;
     if ((rc = e->pos[1].ensure(ns))) return rc;
     if ((rc = e->vel.ensure(ns))) return rc;
@@ -1048,6 +1055,7 @@ int p3d_ipc_export(p3d_engine *e, unsigned char *handles /* 3 * 64 bytes */) {
         CU(cudaIpcGetMemHandle(&h, ptrs[k]));
         std::memcpy(handles + 64 * k, &h, 64);
     }
+    e->ipc_exported = true;
     return P3D_OK;
 }
 
@@ -1062,6 +1070,7 @@ int p3d_ipc_close(p3d_engine *e) {
         for (int k = 0; k < 3; ++k) e->peer_ptr[g][k] = nullptr;
     }
     e->peers_ready = false;
+    e->ipc_exported = false;
     return P3D_OK;
 }
 

@@ -72,6 +72,11 @@ class ShardedStepper:
         self.fused = fused and world > 1
         self._bar = barrier_tensor
 
+    def reset(self):
+        """Call after a re-upload: the engine starts again from its first position buffer."""
+        self._views = [None, None]
+        self._parity = 0
+
     def _tensors(self):
         if self._views[self._parity] is None:
             self._views[self._parity] = self._tensors_fn()

@@ -83,18 +83,21 @@ def measured_peaks():
         return None
 
 
-def workload(n: int, W: float):
+def workload(n: int, W: float, cloud: str = "uniform"):
     import particle_3d as p3
 
     prm = p3.default_params_dict()
     prm["world_size"] = W
+    if cloud == "plummer":  # BASELINE.json's clustered cloud: Plummer radius CDF, scale a = W/6, truncated to the box
+        return prm, p3.generate_plummer(W, n, W / 6, seed=SEED)
     return prm, p3.generate_particles(W, n, seed=SEED)
 
 
-def config_dict(n, W, extra=None):
-    c = {"workload": f"N={n} uniform cloud, W={W} (density 1), default scene constants (main.rs:133-148), ts=1/60, seed {SEED}; "
+def config_dict(n, W, extra=None, cloud="uniform"):
+    what = "uniform cloud" if cloud == "uniform" else "clustered (Plummer a=W/6) cloud"
+    c = {"workload": f"N={n} {what}, W={W} (density 1), default scene constants (main.rs:133-148), ts=1/60, seed {SEED}; "
                      "BASELINE.json configs[3]",
-         "n_particles": n, "world_size": W, "algorithm": "all-pairs (N^2 ordered pairs per step)",
+         "n_particles": n, "world_size": W, "cloud": cloud, "algorithm": "all-pairs (N^2 ordered pairs per step)",
          "cache": "state is ~100 MB (< L2), so a 512 MiB buffer is overwritten between timed steps to flush L2"}
     if extra:
         c.update(extra)
@@ -139,7 +142,7 @@ def run_reference(args):
     if rank != 0:
         return
     n, W = args.n, args.world_size
-    prm, parts = workload(n, W)
+    prm, parts = workload(n, W, args.cloud)
     per_step_budget = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     times, last = [], None
     for s in range(args.warmup + args.steps):
@@ -153,7 +156,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(n, W),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(n, W, cloud=args.cloud),
         "steps_per_s": 1.0 / step_s,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": sample_txt,
                          "ms_per_step": step_s * 1e3,
@@ -186,7 +189,7 @@ def run_engine(args):
         dist.init_process_group(backend="nccl", device_id=torch.device(f"cuda:{local}"))
 
     n, W = args.n, args.world_size
-    prm, parts = workload(n, W)
+    prm, parts = workload(n, W, args.cloud)
     P = p3.Engine.make_params(**prm)
     eng = p3.Engine(local)
     eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_PAIR if n >= 4096 else _abi.FORCE_REFERENCE_ORDER)
@@ -259,7 +262,7 @@ def run_engine(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "force_kernel": "k_force_pair: all N^2 pairs (north_star); the cell list is reported separately",
         "config": config_dict(n, W, {"parallelism": (f"block rows sharded over {world} GPUs; " + ("per step ONE fused kernel does reduce-scatter(forces) + integrate + all-gather(positions) over NVLink peer memory, NCCL only as two 4-byte barrier all-reduces" if fused else "per step all-reduce(forces) + all-gather(positions) over NCCL")) if world > 1 else "1 GPU",
-                                     "block": args.block}),
+                                     "block": args.block}, cloud=args.cloud),
         "steps_per_s": 1e3 / ms_per_step,
         "gpu_launches": int(launches),
         "clocks": clocks.summary,
@@ -365,8 +368,7 @@ def run_engine(args):
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             eng.upload(a_in, prm["id_count"])  # same-size re-upload: device buffers (and IPC mappings) stay put
-            stepper._views = [None, None]
-            stepper._parity = 0
+            stepper.reset()
             stepper.step(P, TS, 1)
             out = eng.download()
         barrier()
@@ -377,6 +379,37 @@ def run_engine(args):
         line["e2e"] = {"value": float(n) * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 28 + n * 4,
                        "d2h_bytes_per_step": n * 28, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                        "api": "per rank: p3d_upload + sharded step + p3d_download on pinned host arrays"}
+
+    # ---------------- the other cloud (north_star: uniform AND clustered clouds at every GPU count) ----------------
+    if not args.no_other_cloud and n >= 4096:
+        other = "plummer" if args.cloud == "uniform" else "uniform"
+        _, parts_o = workload(n, W, other)
+        eng.set_option(_abi.OPT_TIMING, 0)
+        eng.upload(parts_o, prm["id_count"])  # same n: device buffers (and IPC mappings) stay put
+        if stepper:
+            stepper.reset()
+        o_steps = max(1, min(args.steps, 3))
+        one_step()
+        flush.zero_()
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record(stream)
+        for _ in range(o_steps):
+            one_step()
+            flush.zero_()
+        o1.record(stream)
+        barrier()
+        o_ms = o0.elapsed_time(o1) / o_steps
+        if world > 1:
+            tt = torch.tensor([o_ms], device=f"cuda:{local}")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            o_ms = float(tt.item())
+        line["other_cloud"] = {"cloud": other, "what": f"same N, W and constants on a {'clustered (Plummer a=W/6, truncated to the box)' if other == 'plummer' else 'uniform'} cloud",
+                               "steps": o_steps, "warmup": 1, "ms_per_step": o_ms, "steps_per_s": 1e3 / o_ms,
+                               "value": float(n) * n / (o_ms * 1e-3), "unit": UNIT}
+        eng.upload(parts, prm["id_count"])
+        if stepper:
+            stepper.reset()
 
     # ---------------- "next" row: the cell-list path on the same workload ----------------
     # Reported as effective steps/s only: it evaluates ~30 candidates per particle instead of N, so it
@@ -474,6 +507,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-reduce + all-gather instead of the fused P2P kernel")
     ap.add_argument("--no-cells", action="store_true", help="skip the cell-list (SURVEY §8f-1) section")
+    ap.add_argument("--cloud", default="uniform", choices=["uniform", "plummer"],
+                    help="cloud the headline numbers are measured on (the other one is reported in `other_cloud`)")
+    ap.add_argument("--no-other-cloud", action="store_true", help="skip the `other_cloud` section")
     args = ap.parse_args()
     if args.world_size is None:
         args.world_size = W_DEFAULT if args.n == N_DEFAULT else round(float(args.n) ** (1.0 / 3.0), 1)
