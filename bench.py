@@ -38,17 +38,47 @@ UNIT = "interactions/s"
 
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe): an NVML polling
+    thread (5 ms period, so that even a 50 ms multi-GPU step is sampled); nvidia-smi -lms as fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis and all(v.strip().isdigit() for v in vis.split(",")):
+            gpu_index = int(vis.split(",")[gpu_index])
         self.gpu = gpu_index
         self.p = None
+        self.thread = None
+        self.rows = []  # (sm_mhz, power_w, reasons bitmask)
+        self.summary = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+
+    def _poll(self, nv, h):
+        while not self._stop.is_set():
+            try:
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                  nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                  int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+            except Exception:
+                pass
+            self._stop.wait(0.005)
 
     def __enter__(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self._nv, self._h = nv, h
+            self._max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._stop = threading.Event()
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.thread = None
         try:
             self.p = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -58,7 +88,21 @@ class ClockSampler:
         return self
 
     def __exit__(self, *a):
-        self.summary = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            nv = self._nv
+            if self.rows:
+                clk = sorted(r[0] for r in self.rows)
+                bits = 0
+                for r in self.rows:
+                    bits |= r[2]
+                names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                         ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+                self.summary = {"sm_mhz": clk[len(clk) // 2], "sm_min_mhz": clk[0], "sm_max_mhz": self._max,
+                                "reasons": sorted(n for n, b in names if bits & b), "samples": len(self.rows),
+                                "power_w_max": max(r[1] for r in self.rows), "source": "NVML, 5 ms period"}
+            return
         if not self.p:
             return
         self.p.terminate()
@@ -73,7 +117,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[k] for r in rows for k in range(4) if r[4 + k].strip().lower().startswith("active")})
         self.summary = {"sm_mhz": clk[len(clk) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
-                        "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+                        "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows), "source": "nvidia-smi -lms 100"}
 
 
 def measured_peaks():
@@ -253,6 +297,16 @@ def run_engine(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     c1 = eng.counters()
+    clock_summary = clocks.summary
+    if world > 1:  # every rank sampled its own GPU: report the slowest median and the union of the reasons
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks.summary)
+        meds = [c.get("sm_mhz") for c in allc]
+        clock_summary = dict(allc[0], per_rank_sm_mhz=meds,
+                             sm_mhz=min((m for m in meds if m is not None), default=None),
+                             reasons=sorted({r for c in allc for r in c.get("reasons", [])}),
+                             samples=min(c.get("samples", 0) for c in allc),
+                             power_w_max=max((c.get("power_w_max") or 0.0) for c in allc))
     ms_per_step = ms / args.steps
     value = float(n) * n / (ms_per_step * 1e-3)
     launches = (c1["kernels"] - c0["kernels"]) + args.steps  # + the L2-flush fill kernel per step
@@ -265,14 +319,14 @@ def run_engine(args):
                                      "block": args.block}, cloud=args.cloud),
         "steps_per_s": 1e3 / ms_per_step,
         "gpu_launches": int(launches),
-        "clocks": clocks.summary,
+        "clocks": clock_summary,
     }
 
     if world == 1 and rank == 0:
         # ---------------- roofline of the dominant kernel (k_force_pair) ----------------
         prop = torch.cuda.get_device_properties(local)
         peaks = measured_peaks()
-        sm_max_mhz = (peaks or {}).get("sm_max_mhz") or clocks.summary.get("sm_max_mhz") or 1965.0
+        sm_max_mhz = (peaks or {}).get("sm_max_mhz") or clock_summary.get("sm_max_mhz") or 1965.0
         fp32_peak_tf = prop.multi_processor_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
         import ctypes as C
         mb = (C.c_double * 4)()
@@ -295,7 +349,10 @@ def run_engine(args):
                            "tensor/HBM peaks do not bound this kernel (not a dense contraction)",
             "peak_ffma2_microbench_tflops": mb[0] * 2 / 1e12,
             "algorithmic_flops_per_launch": flops, "flop_per_interaction": FLOP_PER_INTERACTION,
-            "kernel_ms": force_ms, "pair_kernel_ms": pair_ms, "bxb_kernel_ms": kern["bxb"] / max(1, kern["steps"]),
+            "kernel_ms": force_ms, "pair_kernel_ms": pair_ms, "bxb_tail_ms": kern["bxb"] / max(1, kern["steps"]),
+            "bxb_note": "k_force_bxb runs BESIDE k_force_pair on an auxiliary stream (alone, under ncu: 5.8 ms = 1.6 % of the step, "
+                        "profiles/r01_launches_n1048576.csv); pair_kernel_ms therefore contains it and bxb_tail_ms is only what "
+                        "remains after the pair kernel ended",
             "partition_ms": kern["partition"] / max(1, kern["steps"]),
             "interactions_per_s_force_pass": float(n) * n / (force_ms * 1e-3),
             "traffic": prof.get("dram_bytes_per_launch"),
