@@ -525,7 +525,7 @@ int launch_force(p3d_engine *e, const DevParams &P) {
 #define P3D_PAIR_ARGS sx, sy, sz, e->sidx.p, e->bclass.p, e->seg_type.p, M, e->rank, e->world, splits, e->frc.p, P, e->matrix.p, flag_cur
         // MPOS: min_pull_ratio > 0 lets the kernel fold c2*m into the matrix scalars (one FFMA2 fewer per pack)
         const bool mpos = P.m > 0.0f && P.m < 1.0f;
-#define P3D_PAIR_LAUNCH(R_, RC_, MP_) k_force_pair<R_, RC_, 16, 1, MP_><<<grid, 32, 0, st>>>(P3D_PAIR_ARGS)
+#define P3D_PAIR_LAUNCH(R_, RC_, MP_) k_force_pair<R_, RC_, (R_ == 8 ? 12 : 16), 1, MP_><<<grid, 32, 0, st>>>(P3D_PAIR_ARGS)
         if (B == 128) {
             if (P.rcut) { if (mpos) P3D_PAIR_LAUNCH(4, true, true); else P3D_PAIR_LAUNCH(4, true, false); }
             else        { if (mpos) P3D_PAIR_LAUNCH(4, false, true); else P3D_PAIR_LAUNCH(4, false, false); }

@@ -191,7 +191,7 @@ struct PairConsts {
     float2 nim;    // -1/m
     float2 neg1;   // -1
     float2 tiny;   // 1e-30: keeps rsqrt finite at d2 == 0 (self pair, coincident particles)
-    float c2m;     // c2*m: folded into the matrix scalars when m > 0 (see pair_pack, MPOS)
+    float c2m;     // c2*m: folded into the matrix scalars when m > 0 (see pair_group, MPOS)
 };
 
 __device__ __forceinline__ PairConsts make_pair_consts(const DevParams &P) {
@@ -207,51 +207,69 @@ __device__ __forceinline__ PairConsts make_pair_consts(const DevParams &P) {
     return c;
 }
 
-// One i-particle against the lane's two j-particles (one packed register pair per coordinate).
+// G i-particles against the lane's two j-particles (one packed register pair per coordinate), evaluated
+// STAGE BY STAGE across the G particles: all relative positions, all squared distances, all rsqrt, all
+// force-law scalars, then the accumulations (i-side particle by particle, then the three dependent j-side
+// chains).  Same arithmetic per pair as a particle-by-particle loop; the staged order is what lets ptxas
+// issue the j-side chains and their shuffles early and fill the shuffle latency with the long run of
+// independent i-side FFMA2 (6 % faster than the per-particle order on B200).
 // The i-position enters as a broadcast scalar operand of FADD2 (SASS: `-R.F32`), so it needs no
-// duplication.  17 packed FP32 instructions + 2 MUFU.RSQ + 6 FMNMX for four ordered interactions.
-// The accumulation order alternates i/j so that consecutive FFMA2 share a source register pair
-// (operand-reuse cache): an FFMA2 that reads three distinct register pairs costs 3 cycles, not 2.
-template <bool RCUT, bool SYM, bool MPOS>
-__device__ __forceinline__ void pair_pack(const float2 jx, const float2 jy, const float2 jz, const float nix,
-                                          const float niy, const float niz, const PairConsts &c,
-                                          const float2 aij, const float2 aji, const float r2, float2 &aix,
-                                          float2 &aiy, float2 &aiz, float2 &ajx, float2 &ajy, float2 &ajz) {
-    const float2 dx = __fadd2_rn(jx, dup2(nix));  // other.position - position (src/lib.rs:211-212, offset 0)
-    const float2 dy = __fadd2_rn(jy, dup2(niy));
-    const float2 dz = __fadd2_rn(jz, dup2(niz));
-    float2 d2 = __ffma2_rn(dx, dx, c.tiny);
-    d2 = __ffma2_rn(dy, dy, d2);
-    d2 = __ffma2_rn(dz, dz, d2);
-    const float2 inv = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
-    float2 rs = __ffma2_rn(inv, c.neg1, c.im);        // u = 1/m - 1/d
-    float2 ti;
-    if (MPOS) {
-        const float2 p2 = __ffma2_rn(inv, c.im, c.nim);   // (1/d - 1) / m
-        ti = make_float2(fmaxf(fminf(rs.x, p2.x), 0.0f), fmaxf(fminf(rs.y, p2.y), 0.0f));
-    } else {
-        const float2 p1 = __ffma2_rn(inv, c.ncm, c.c2);   // c2 * (1 - m/d)
-        const float2 p2 = __ffma2_rn(inv, c.c2, c.nc2);   // c2 * (1/d - 1)
-        ti = make_float2(fmaxf(fminf(p1.x, p2.x), 0.0f), fmaxf(fminf(p1.y, p2.y), 0.0f));
+// duplication.  Per i-particle: 16 packed FP32 instructions (17 without MPOS) + 2 MUFU.RSQ + 6 FMNMX for
+// four ordered interactions.
+template <int G, bool RCUT, bool MPOS>
+__device__ __forceinline__ void pair_group(const float2 jx, const float2 jy, const float2 jz, const float *nix,
+                                           const float *niy, const float *niz, const PairConsts &c,
+                                           const float2 aij, const float2 aji, const float r2, float2 *aix,
+                                           float2 *aiy, float2 *aiz, float2 &ajx, float2 &ajy, float2 &ajz) {
+    float2 dx[G], dy[G], dz[G], sij[G], sji[G];
+    float2 d2[G], inv[G], rs[G], ti[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        dx[g] = __fadd2_rn(jx, dup2(nix[g]));  // other.position - position (src/lib.rs:211-212, offset 0)
+        dy[g] = __fadd2_rn(jy, dup2(niy[g]));
+        dz[g] = __fadd2_rn(jz, dup2(niz[g]));
     }
-    rs = make_float2(fminf(rs.x, 0.0f), fminf(rs.y, 0.0f));
-    if (RCUT) {  // r < 1: src/lib.rs:216-220 cuts inside the force range
-        if (!(d2.x < r2)) { ti.x = 0.0f; rs.x = 0.0f; }
-        if (!(d2.y < r2)) { ti.y = 0.0f; rs.y = 0.0f; }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        d2[g] = __ffma2_rn(dx[g], dx[g], c.tiny);
+        d2[g] = __ffma2_rn(dy[g], dy[g], d2[g]);
+        d2[g] = __ffma2_rn(dz[g], dz[g], d2[g]);
     }
-    const float2 sij = __ffma2_rn(aij, ti, rs);       // f(d; A[i][j]) / d
-    if (SYM) {
-        const float2 sji = __ffma2_rn(aji, ti, rs);   // f(d; A[j][i]) / d
-        aix = __ffma2_rn(dx, sij, aix);               // acc += rel / d * f  (src/lib.rs:231)
-        ajx = __ffma2_rn(dx, sji, ajx);               // negated when flushed: rel_ji = -rel_ij
-        ajy = __ffma2_rn(dy, sji, ajy);
-        aiy = __ffma2_rn(dy, sij, aiy);
-        aiz = __ffma2_rn(dz, sij, aiz);
-        ajz = __ffma2_rn(dz, sji, ajz);
-    } else {
-        aix = __ffma2_rn(dx, sij, aix);
-        aiy = __ffma2_rn(dy, sij, aiy);
-        aiz = __ffma2_rn(dz, sij, aiz);
+#pragma unroll
+    for (int g = 0; g < G; ++g) inv[g] = make_float2(rsqrt_approx(d2[g].x), rsqrt_approx(d2[g].y));
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        rs[g] = __ffma2_rn(inv[g], c.neg1, c.im);            // u = 1/m - 1/d
+        if (MPOS) {
+            const float2 p2 = __ffma2_rn(inv[g], c.im, c.nim);   // (1/d - 1) / m
+            ti[g] = make_float2(fmaxf(fminf(rs[g].x, p2.x), 0.0f), fmaxf(fminf(rs[g].y, p2.y), 0.0f));
+        } else {
+            const float2 p1 = __ffma2_rn(inv[g], c.ncm, c.c2);   // c2 * (1 - m/d)
+            const float2 p2 = __ffma2_rn(inv[g], c.c2, c.nc2);   // c2 * (1/d - 1)
+            ti[g] = make_float2(fmaxf(fminf(p1.x, p2.x), 0.0f), fmaxf(fminf(p1.y, p2.y), 0.0f));
+        }
+        rs[g] = make_float2(fminf(rs[g].x, 0.0f), fminf(rs[g].y, 0.0f));
+        if (RCUT) {  // r < max(1, m): src/lib.rs:216-220 cuts inside the force range
+            if (!(d2[g].x < r2)) { ti[g].x = 0.0f; rs[g].x = 0.0f; }
+            if (!(d2[g].y < r2)) { ti[g].y = 0.0f; rs[g].y = 0.0f; }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        sij[g] = __ffma2_rn(aij, ti[g], rs[g]);   // f(d; A[i][j]) / d
+        sji[g] = __ffma2_rn(aji, ti[g], rs[g]);   // f(d; A[j][i]) / d
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        aix[g] = __ffma2_rn(dx[g], sij[g], aix[g]);   // acc += rel / d * f  (src/lib.rs:231)
+        aiy[g] = __ffma2_rn(dy[g], sij[g], aiy[g]);
+        aiz[g] = __ffma2_rn(dz[g], sij[g], aiz[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        ajx = __ffma2_rn(dx[g], sji[g], ajx);         // negated when flushed: rel_ji = -rel_ij
+        ajy = __ffma2_rn(dy[g], sji[g], ajy);
+        ajz = __ffma2_rn(dz[g], sji[g], ajz);
     }
 }
 
@@ -318,10 +336,7 @@ k_force_pair(const float *__restrict__ sx, const float *__restrict__ sy, const f
             float2 ajx = make_float2(0.f, 0.f), ajy = ajx, ajz = ajx;
 #pragma unroll 1
             for (int step = 0; step < 32; ++step) {
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-                    pair_pack<RCUT, true, MPOS>(jx, jy, jz, nix[r], niy[r], niz[r], c, aij, aji, P.r2, aix[r], aiy[r],
-                                          aiz[r], ajx, ajy, ajz);
+                pair_group<R, RCUT, MPOS>(jx, jy, jz, nix, niy, niz, c, aij, aji, P.r2, aix, aiy, aiz, ajx, ajy, ajz);
                 jx = shfl2(jx, next); jy = shfl2(jy, next); jz = shfl2(jz, next);
                 ajx = shfl2(ajx, next); ajy = shfl2(ajy, next); ajz = shfl2(ajz, next);
             }
