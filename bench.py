@@ -35,6 +35,23 @@ FLOP_PER_INTERACTION = 20  # north_star's convention
 METRIC = "pair_interactions_per_s"
 UNIT = "interactions/s"
 
+# stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version banner,
+# for one) is sent to stderr by pointing fd 1 at fd 2 for the duration of the run.
+_JSON_FD = None
+
+
+def _capture_stdout():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
 
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -209,7 +226,7 @@ def run_reference(args):
         "note": "all-pairs-equivalent N^2/t of the reference's cell-list algorithm; the Rust crate itself cannot be "
                 "built here (no cargo/rustc), this is the C restatement oracle/p3d_oracle.c",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -350,7 +367,7 @@ def run_engine(args):
             "peak_ffma2_microbench_tflops": mb[0] * 2 / 1e12,
             "algorithmic_flops_per_launch": flops, "flop_per_interaction": FLOP_PER_INTERACTION,
             "kernel_ms": force_ms, "pair_kernel_ms": pair_ms, "bxb_tail_ms": kern["bxb"] / max(1, kern["steps"]),
-            "bxb_note": "k_force_bxb runs BESIDE k_force_pair on an auxiliary stream (alone, under ncu: 5.8 ms = 1.6 % of the step, "
+            "bxb_note": "k_force_bxb runs BESIDE k_force_pair on an auxiliary stream (alone, under ncu: 5.8 ms = 1.7 % of the step, "
                         "profiles/r01_launches_n1048576.csv); pair_kernel_ms therefore contains it and bxb_tail_ms is only what "
                         "remains after the pair kernel ended",
             "partition_ms": kern["partition"] / max(1, kern["steps"]),
@@ -543,7 +560,7 @@ def run_engine(args):
             "candidate_pairs_per_s": r["candidates_per_particle"] * n / r["step_s"],
         }
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -572,6 +589,7 @@ def main():
         args.world_size = W_DEFAULT if args.n == N_DEFAULT else round(float(args.n) ** (1.0 / 3.0), 1)
     if args.warmup < 3:
         args.warmup = 3  # timing rules: at least 3 warm-up steps
+    _capture_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
