@@ -92,7 +92,7 @@ struct p3d_engine {
     std::vector<int> seg_start_h, seg_end_h;
 
     DevBuf<float4> pos[2], vel, frc, spos;
-    DevBuf<uint32_t> slot_of, sidx;
+    DevBuf<uint32_t> slot_of, sidx, type_cnt;  // type_cnt: per-CTA type counts, offsets and totals of the layout sort
     DevBuf<uint8_t> seg_type, bclass;
     DevBuf<int> seg_start, seg_end, cnt;
     DevBuf<int2> cta_cnt, cta_off;
@@ -108,7 +108,7 @@ struct p3d_engine {
     int cur = 0;            // which pos buffer is current
     int parity = 0;         // which flag word describes the current positions
 
-    std::vector<uint32_t> slot_h;
+    std::vector<uint8_t> seg_type_h;
 
     // options
     int opt_force = P3D_FORCE_AUTO;
@@ -215,14 +215,36 @@ int build_layout_identity(p3d_engine *e, size_t n, uint32_t T) {
     return P3D_OK;
 }
 
-int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T) {
+// Type-grouped layout for the pair kernel.  The counting sort by type id runs on the device (k_type_hist,
+// k_type_scan, later k_pack_typed); the host only sees the T per-type totals, from which it derives the
+// block-padded segments.  Copies `in` to the device (the counts need it) and returns with the stream idle.
+int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T, bool timed) {
     if (n > (size_t)0x7fff0000) return fail(P3D_ERR_INVALID, "n too large");
-    std::vector<size_t> count(T, 0);
-    for (size_t i = 0; i < n; ++i) {
-        const uint32_t id = in[i].id;
-        if (id >= T)
-            return fail(P3D_ERR_BAD_ID, "particle %zu has id %u >= id_count %u (src/lib.rs:225-228)", i, id, T);
-        ++count[id];
+    static_assert(P3D_MAX_TYPES == kTypeMax, "k_type_* kernels are sized for P3D_MAX_TYPES");
+    cudaStream_t st = e->stream;
+    int rc;
+    const size_t n_ctas = (n + kTypeThreads - 1) / kTypeThreads;
+    if ((rc = e->aos.ensure((n ? n : 1) * 7))) return rc;
+    if ((rc = e->type_cnt.ensure(2 * std::max<size_t>(n_ctas, 1) * T + P3D_MAX_TYPES))) return rc;
+    if ((rc = e->flags.ensure(4))) return rc;
+    uint32_t *cta_cnt = e->type_cnt.p, *cta_off = cta_cnt + n_ctas * T, *total = cta_off + n_ctas * T;
+    std::vector<uint32_t> count(T, 0);
+    if (n) {
+        CU(cudaMemcpyAsync(e->aos.p, in, n * sizeof(p3d_particle), cudaMemcpyHostToDevice, st));
+        if (timed) CU(cudaEventRecord(e->ev_call[1], st));
+        CU(cudaMemsetAsync(e->flags.p + 2, 0x7f, sizeof(int), st));  // 0x7f7f7f7f: larger than any index
+        k_type_hist<<<(unsigned)n_ctas, kTypeThreads, 0, st>>>(e->aos.p, (int)n, T, cta_cnt, e->flags.p + 2);
+        k_type_scan<<<T, 1024, 0, st>>>(cta_cnt, cta_off, (int)n_ctas, T, total);
+        e->counters[0] += 2;
+        CU(cudaGetLastError());
+        int bad = 0;
+        CU(cudaMemcpyAsync(count.data(), total, T * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&bad, e->flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if ((size_t)bad < n)
+            return fail(P3D_ERR_BAD_ID, "particle %d has id %u >= id_count %u (src/lib.rs:225-228)", bad, in[bad].id, T);
+    } else if (timed) {
+        CU(cudaEventRecord(e->ev_call[1], st));
     }
     e->typed = true;
     e->layout_version++;
@@ -233,7 +255,7 @@ int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T) {
     size_t at = 0;
     for (uint32_t t = 0; t < T; ++t) {
         e->seg_start_h[t] = (int)at;
-        at += (count[t] + B - 1) / B * B;
+        at += ((size_t)count[t] + B - 1) / B * B;
         e->seg_end_h[t] = (int)at;
     }
     if (at == 0) at = B;  // keep one (ghost) block so kernels always have a valid grid
@@ -246,16 +268,11 @@ int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T) {
     e->M = e->n_slots / B;
     e->n = n;
     e->T = T;
-    std::vector<uint8_t> seg_type_h(e->M, 0);
+    e->seg_type_h.assign(e->M, 0);
     for (uint32_t t = 0; t < T; ++t)
-        for (int b = e->seg_start_h[t] / B; b < e->seg_end_h[t] / B; ++b) seg_type_h[b] = (uint8_t)t;
-    e->slot_h.resize(n);
-    std::vector<size_t> cursor(T);
-    for (uint32_t t = 0; t < T; ++t) cursor[t] = (size_t)e->seg_start_h[t];
-    for (size_t i = 0; i < n; ++i) e->slot_h[i] = (uint32_t)cursor[in[i].id]++;  // stable within a type
+        for (int b = e->seg_start_h[t] / B; b < e->seg_end_h[t] / B; ++b) e->seg_type_h[b] = (uint8_t)t;
 
     const size_t ns = (size_t)e->n_slots;
-    int rc;
     if (e->ipc_exported && ((size_t)ns > e->pos[0].cap || (size_t)ns > e->pos[1].cap || (size_t)ns > e->frc.cap))
         return fail(P3D_ERR_INVALID, "upload needs %zu slots but the position/force buffers are exported to peer GPUs "
                     "(p3d_ipc_export); call p3d_ipc_close on every rank, upload, then export/import again", (size_t)ns);
@@ -276,19 +293,14 @@ int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T) {
     if ((rc = e->cnt.ensure(2 * P3D_MAX_TYPES))) return rc;
     if ((rc = e->cta_cnt.ensure(ns / kPartThreads + 1))) return rc;
     if ((rc = e->cta_off.ensure(ns / kPartThreads + 1))) return rc;
-    if ((rc = e->aos.ensure((n ? n : 1) * 7))) return rc;
     if ((rc = e->matrix.ensure(P3D_MAX_TYPES * P3D_MAX_TYPES))) return rc;
-    if ((rc = e->flags.ensure(4))) return rc;
     if ((rc = e->diag.ensure(8))) return rc;
 
-    cudaStream_t st = e->stream;
-    CU(cudaMemcpyAsync(e->seg_type.p, seg_type_h.data(), (size_t)e->M, cudaMemcpyHostToDevice, st));
+    // small host arrays owned by the engine (they stay valid until the next upload, which first drains the stream)
+    CU(cudaMemcpyAsync(e->seg_type.p, e->seg_type_h.data(), (size_t)e->M, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(e->seg_start.p, e->seg_start_h.data(), T * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(e->seg_end.p, e->seg_end_h.data(), T * sizeof(int), cudaMemcpyHostToDevice, st));
-    if (n) CU(cudaMemcpyAsync(e->slot_of.p, e->slot_h.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(e->flags.p, 0, 4 * sizeof(int), st));
-    // seg_type_h / slot_h are pageable: the copies above are staged synchronously by the runtime
-    CU(cudaStreamSynchronize(st));
     return P3D_OK;
 }
 
@@ -299,9 +311,14 @@ int launch_pack(p3d_engine *e, size_t n) {
     e->parity = 0;
     k_fill_ghosts<<<(ns + 255) / 256, 256, 0, st>>>(e->pos[0].p, e->pos[1].p, e->vel.p, e->frc.p, ns);
     e->counters[0]++;
-    if (n) {
-        k_pack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->aos.p, e->typed ? e->slot_of.p : nullptr, e->pos[0].p,
-                                                            e->vel.p, (int)n, e->T, e->flags.p + 2);
+    if (n && e->typed) {
+        const uint32_t *cta_off = e->type_cnt.p + (n + kTypeThreads - 1) / kTypeThreads * e->T;
+        k_pack_typed<<<(unsigned)((n + kTypeThreads - 1) / kTypeThreads), kTypeThreads, 0, st>>>(
+            e->aos.p, (int)n, e->T, e->seg_start.p, cta_off, e->pos[0].p, e->vel.p, e->slot_of.p);
+        e->counters[0]++;
+    } else if (n) {
+        k_pack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->aos.p, nullptr, e->pos[0].p, e->vel.p, (int)n, e->T,
+                                                            e->flags.p + 2);
         e->counters[0]++;
     }
     CU(cudaGetLastError());
@@ -753,7 +770,7 @@ void p3d_destroy(p3d_engine *e) {
     p3d_ipc_close(e);
     for (auto &b : e->pos) b.release();
     e->vel.release(); e->frc.release(); e->spos.release();
-    e->slot_of.release(); e->sidx.release();
+    e->slot_of.release(); e->sidx.release(); e->type_cnt.release();
     e->seg_type.release(); e->bclass.release();
     e->seg_start.release(); e->seg_end.release(); e->cnt.release(); e->cta_cnt.release(); e->cta_off.release();
     for (auto &b : e->ckeys) b.release();
@@ -815,17 +832,19 @@ int p3d_upload(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t id_coun
         return fail(P3D_ERR_INVALID, "id_count %u outside 1..%d", id_count, P3D_MAX_TYPES);
     CU(cudaSetDevice(e->device));
     int rc;
-    // The pair kernel needs type-grouped slots (host counting sort); every other kernel runs on the
-    // identity layout, which costs no host pass at all.
-    if (resolve_force_kernel_for(e, n) == P3D_FORCE_PAIR) rc = build_layout(e, in, n, id_count);
-    else rc = build_layout_identity(e, n, id_count);
-    if (rc) return rc;
     if (e->opt_timing) {
         if ((rc = ensure_events(e, 1))) return rc;
         CU(cudaEventRecord(e->ev_call[0], e->stream));
     }
-    if (n) CU(cudaMemcpyAsync(e->aos.p, in, n * sizeof(p3d_particle), cudaMemcpyHostToDevice, e->stream));
-    if (e->opt_timing) CU(cudaEventRecord(e->ev_call[1], e->stream));
+    // The pair kernel needs type-grouped slots (a counting sort by type id, done on the device); every other
+    // kernel runs on the identity layout.  Either way there is no host pass over the particles.
+    if (resolve_force_kernel_for(e, n) == P3D_FORCE_PAIR) {
+        if ((rc = build_layout(e, in, n, id_count, e->opt_timing != 0))) return rc;  // copies `in` itself
+    } else {
+        if ((rc = build_layout_identity(e, n, id_count))) return rc;
+        if (n) CU(cudaMemcpyAsync(e->aos.p, in, n * sizeof(p3d_particle), cudaMemcpyHostToDevice, e->stream));
+        if (e->opt_timing) CU(cudaEventRecord(e->ev_call[1], e->stream));
+    }
     if ((rc = launch_pack(e, n))) return rc;
     if (e->opt_timing) CU(cudaEventRecord(e->ev_call[2], e->stream));
     // `in` may be pageable or reused by the caller: the copy must have consumed it before we return.

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) k_fill_ghosts(float4 *__restrict__ pos0, 
     frc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// K3b: AoS (28 B, caller's index order) -> SoA float4 slots (type-sorted).  The block stages its
+// K3b: AoS (28 B, caller's index order) -> SoA float4 slots.  The block stages its
 // 256 structs through shared memory so that the global reads are fully coalesced 4-byte streams;
 // the per-thread reads from shared memory have stride 7 words (co-prime with 32 banks).
 // slot_of == nullptr: identity layout (slot = caller index); ids are then validated here
@@ -44,6 +44,103 @@ __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, con
     if (f2u(p[6]) >= id_count) atomicOr(err, 1);
     pos[s] = make_float4(p[0], p[1], p[2], p[6]);  // w carries the id bits
     vel[s] = make_float4(p[3], p[4], p[5], 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Type-grouped layout, built on the device (the pair kernel needs type-pure blocks): a stable counting
+// sort of the caller's particles by type id.  k_type_hist counts ids per 256-particle CTA and validates
+// them, k_type_scan turns the per-CTA counts of each type into exclusive offsets, k_pack_typed recomputes
+// each particle's rank inside its CTA and writes it to slot seg_start[id] + offset + rank.  Within a type
+// the slots ascend with the caller's index, so every rank of a multi-GPU run derives the same layout.
+constexpr int kTypeThreads = 256;
+constexpr int kTypeMax = 64;  // == P3D_MAX_TYPES
+
+// bad[0]: smallest caller index whose id >= id_count (the condition src/lib.rs:225-228 would index out
+// of bounds on); stays INT_MAX when all ids are valid.
+__global__ void __launch_bounds__(kTypeThreads) k_type_hist(const float *__restrict__ aos, int n, uint32_t id_count,
+                                                            uint32_t *__restrict__ cta_cnt, int *__restrict__ bad) {
+    __shared__ uint32_t h[kTypeMax];
+    if (threadIdx.x < kTypeMax) h[threadIdx.x] = 0u;
+    __syncthreads();
+    const int i = blockIdx.x * kTypeThreads + threadIdx.x;
+    if (i < n) {
+        const uint32_t id = f2u(aos[(size_t)i * 7 + 6]);
+        if (id >= id_count) atomicMin(bad, i);
+        else atomicAdd(&h[id], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < id_count) cta_cnt[(size_t)blockIdx.x * id_count + threadIdx.x] = h[threadIdx.x];
+}
+
+// One CTA per type: exclusive prefix over the CTAs of that type's counts; total[t] = particles of type t.
+__global__ void __launch_bounds__(1024) k_type_scan(const uint32_t *__restrict__ cta_cnt, uint32_t *__restrict__ cta_off,
+                                                    int n_ctas, uint32_t id_count, uint32_t *__restrict__ total) {
+    const uint32_t t = blockIdx.x;
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n_ctas; base += 1024) {
+        const int c = base + threadIdx.x;
+        const uint32_t v = (c < n_ctas) ? cta_cnt[(size_t)c * id_count + t] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += a;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = warp_tot[lane];
+            uint32_t winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t a = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += a;
+            }
+            warp_tot[lane] = winc - w;
+        }
+        __syncthreads();
+        const uint32_t cbase = carry, wbase = warp_tot[warp];
+        if (c < n_ctas) cta_off[(size_t)c * id_count + t] = cbase + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = cbase + wbase + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[t] = carry;
+}
+
+// AoS -> type-grouped SoA slots; also records slot_of[caller index] for the way back (k_unpack).
+__global__ void __launch_bounds__(kTypeThreads) k_pack_typed(const float *__restrict__ aos, int n, uint32_t id_count,
+                                                             const int *__restrict__ seg_start,
+                                                             const uint32_t *__restrict__ cta_off,
+                                                             float4 *__restrict__ pos, float4 *__restrict__ vel,
+                                                             uint32_t *__restrict__ slot_of) {
+    __shared__ float sm[kTypeThreads * 7];
+    __shared__ uint32_t wcnt[kTypeThreads / 32][kTypeMax];
+    const int base = blockIdx.x * kTypeThreads;
+    const int cnt = min(kTypeThreads, n - base);
+    const float *src = aos + (size_t)base * 7;
+    for (int w = threadIdx.x; w < cnt * 7; w += kTypeThreads) sm[w] = src[w];
+    for (int w = threadIdx.x; w < (kTypeThreads / 32) * kTypeMax; w += kTypeThreads) (&wcnt[0][0])[w] = 0u;
+    __syncthreads();
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const bool valid = t < cnt;
+    const float *p = sm + t * 7;
+    const uint32_t id = valid ? f2u(p[6]) : 0xFFFFFFFFu;  // ids were validated by k_type_hist
+    const unsigned same = __match_any_sync(0xffffffffu, id);
+    const int rank = __popc(same & ((1u << lane) - 1u));
+    if (valid && rank == 0) wcnt[warp][id] = (uint32_t)__popc(same);
+    __syncthreads();
+    if (!valid) return;
+    uint32_t before = 0u;
+    for (int w = 0; w < warp; ++w) before += wcnt[w][id];
+    const uint32_t s = (uint32_t)seg_start[id] + cta_off[(size_t)blockIdx.x * id_count + id] + before + (uint32_t)rank;
+    pos[s] = make_float4(p[0], p[1], p[2], p[6]);  // w carries the id bits
+    vel[s] = make_float4(p[3], p[4], p[5], 0.f);
+    slot_of[base + t] = s;
 }
 
 // K3c: SoA slots -> AoS in the caller's index order (src/lib.rs:268: index order preserved).

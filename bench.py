@@ -429,7 +429,7 @@ def run_engine(args):
             eng.update_into(P, TS, a_in, a_out)  # synchronous: H2D + step + D2H
             a_in, a_out = a_out, a_in            # src/lib.rs:167 swap
         e2e_s = (time.perf_counter() - t0) / e2e_steps
-        line["e2e"] = {"value": float(n) * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 28 + n * 4,
+        line["e2e"] = {"value": float(n) * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 28,
                        "d2h_bytes_per_step": n * 28, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                        "api": "p3d_update(engine, params, ts, in, out, n) on pinned host arrays; wall clock around the synchronous call"}
     else:
@@ -450,7 +450,7 @@ def run_engine(args):
         tt = torch.tensor([e2e_s], device=f"cuda:{local}")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
-        line["e2e"] = {"value": float(n) * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 28 + n * 4,
+        line["e2e"] = {"value": float(n) * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 28,
                        "d2h_bytes_per_step": n * 28, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                        "api": "per rank: p3d_upload + sharded step + p3d_download on pinned host arrays"}
 
