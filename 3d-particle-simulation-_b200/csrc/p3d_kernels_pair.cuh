@@ -369,6 +369,11 @@ __device__ __forceinline__ float nearest_image2(float q, float p0, float pa) {
 // (`other.position - (position + offset)` with the f32 rounding of position + offset); the force law
 // is the same branch-free rsqrt form as k_force_pair.  All particles are inside the box here (the
 // flag check), so per axis only offsets 0 and -sign(p)*W can be within reach.
+// Two passes per four j: the distance through the nearest image only needs MAGNITUDES
+// (min(|q - p|, |q - (p + offset)|) per axis: two FADD and one FMNMX), so the signed image selection, the
+// rsqrt, the matrix lookup and the accumulation run only when some lane of the warp has one of its four
+// pairs within reach (the reference's own `d2 < r^2` test, src/lib.rs:216-220; beyond reach the force is
+// exactly zero) — about 7 % of the warp iterations at density 1.
 // grid = (rows of this shard, jsplit): CTA (x, y) takes every jsplit-th boundary block.
 template <int B, bool RCUT>
 __global__ void __launch_bounds__(B) k_force_bxb(const float4 *__restrict__ spos, const uint32_t *__restrict__ sidx,
@@ -385,6 +390,7 @@ __global__ void __launch_bounds__(B) k_force_bxb(const float4 *__restrict__ spos
     float *smat = reinterpret_cast<float *>(sm_dyn + B);
     for (int k = threadIdx.x; k < P.T * P.T; k += B) smat[k] = matrix[k];
 
+    // ghost i-slots (1e15 away from everything) walk the loop too, so that warp votes see all 32 lanes
     const float4 pi = spos[row * B + threadIdx.x];
     const uint32_t idi = f2u(pi.w);
     const bool live = idi != P3D_GHOST_ID;
@@ -394,6 +400,7 @@ __global__ void __launch_bounds__(B) k_force_bxb(const float4 *__restrict__ spos
     const float pza = __fadd_rn(pi.z, pi.z > 0.f ? -P.W : P.W);
     const uint32_t mrow = live ? idi * (uint32_t)P.T : 0u;
     const float c2 = P.c2, ncm = -P.c2 * P.m, nc2 = -P.c2, im = P.inv_m, r2 = P.r2;
+    const float reach2 = P.reach * P.reach * 1.000001f;  // a hair wide: pairs at the very edge take the exact path
     float ax = 0.f, ay = 0.f, az = 0.f;
     int visit = 0;
     for (int t = 0; t < P.T; ++t) {
@@ -406,29 +413,41 @@ __global__ void __launch_bounds__(B) k_force_bxb(const float4 *__restrict__ spos
             __syncthreads();
             tile[threadIdx.x] = spos[b * B + threadIdx.x];
             __syncthreads();
-            if (!live) continue;
             const float *arow = smat + mrow;
-#pragma unroll 4
-            for (int k = 0; k < B; ++k) {
-                const float4 q = tile[k];
-                const float rx = nearest_image2(q.x, pi.x, pxa);
-                const float ry = nearest_image2(q.y, pi.y, pya);
-                const float rz = nearest_image2(q.z, pi.z, pza);
-                const float d2 = fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, 1.0e-30f)));
-                const float inv = rsqrt_approx(d2);
-                const float p1 = fmaf(inv, ncm, c2), p2 = fmaf(inv, c2, nc2);
-                float ti = fmaxf(fminf(p1, p2), 0.0f);
-                float rs = fminf(im - inv, 0.0f);
-                if (RCUT) {
-                    if (!(d2 < r2)) { ti = 0.0f; rs = 0.0f; }
+#pragma unroll 2
+            for (int k0 = 0; k0 < B; k0 += 4) {
+                bool near = false;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 q = tile[k0 + k];
+                    const float mx = fminf(fabsf(__fsub_rn(q.x, pi.x)), fabsf(__fsub_rn(q.x, pxa)));
+                    const float my = fminf(fabsf(__fsub_rn(q.y, pi.y)), fabsf(__fsub_rn(q.y, pya)));
+                    const float mz = fminf(fabsf(__fsub_rn(q.z, pi.z)), fabsf(__fsub_rn(q.z, pza)));
+                    near |= fmaf(mz, mz, fmaf(my, my, mx * mx)) < reach2;
                 }
-                // ghosts (type id 0xFFFFFFFF) sit 1e15 away: ti = rs = 0, so any matrix entry will do
-                const uint32_t tj = f2u(q.w);
-                const float a = arow[tj < (uint32_t)P.T ? tj : 0u];
-                const float s = fmaf(a, ti, rs);
-                ax = fmaf(rx, s, ax);
-                ay = fmaf(ry, s, ay);
-                az = fmaf(rz, s, az);
+                if (!__any_sync(0xffffffffu, near)) continue;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 q = tile[k0 + k];
+                    const float rx = nearest_image2(q.x, pi.x, pxa);
+                    const float ry = nearest_image2(q.y, pi.y, pya);
+                    const float rz = nearest_image2(q.z, pi.z, pza);
+                    const float d2 = fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, 1.0e-30f)));
+                    const float inv = rsqrt_approx(d2);
+                    const float p1 = fmaf(inv, ncm, c2), p2 = fmaf(inv, c2, nc2);
+                    float ti = fmaxf(fminf(p1, p2), 0.0f);
+                    float rs = fminf(im - inv, 0.0f);
+                    if (RCUT) {
+                        if (!(d2 < r2)) { ti = 0.0f; rs = 0.0f; }
+                    }
+                    // ghosts (type id 0xFFFFFFFF) sit 1e15 away: ti = rs = 0, so any matrix entry will do
+                    const uint32_t tj = f2u(q.w);
+                    const float a = arow[tj < (uint32_t)P.T ? tj : 0u];
+                    const float s = fmaf(a, ti, rs);
+                    ax = fmaf(rx, s, ax);
+                    ay = fmaf(ry, s, ay);
+                    az = fmaf(rz, s, az);
+                }
             }
         }
     }

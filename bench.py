@@ -367,7 +367,7 @@ def run_engine(args):
             "peak_ffma2_microbench_tflops": mb[0] * 2 / 1e12,
             "algorithmic_flops_per_launch": flops, "flop_per_interaction": FLOP_PER_INTERACTION,
             "kernel_ms": force_ms, "pair_kernel_ms": pair_ms, "bxb_tail_ms": kern["bxb"] / max(1, kern["steps"]),
-            "bxb_note": "k_force_bxb runs BESIDE k_force_pair on an auxiliary stream (alone, under ncu: 5.8 ms = 1.7 % of the step, "
+            "bxb_note": "k_force_bxb runs BESIDE k_force_pair on an auxiliary stream (alone, under ncu: 2.2 ms = 0.7 % of the step, "
                         "profiles/r01_launches_n1048576.csv); pair_kernel_ms therefore contains it and bxb_tail_ms is only what "
                         "remains after the pair kernel ended",
             "partition_ms": kern["partition"] / max(1, kern["steps"]),

@@ -7,7 +7,8 @@ profiles/r01_drift_config3.json: pair kernel, cell list and CPU oracle all drift
 same rate).  The stated bound is therefore calibrated on the oracle's own sensitivity: the CPU oracle run twice,
 with f32 and with f64 force accumulation, gives the envelope E(t) = |KE_f32 - KE_f64| / KE; the GPU must stay
 within max(20 * E(t), floor(t)) of the f32 oracle, floor = 1e-6 up to 50 steps and 1e-4 * (t/100)^2 later, and the
-time-averaged kinetic energy over each 100-step window must agree within the window's own fluctuation.
+time-averaged kinetic energy over each 100-step window must agree within the window's own fluctuation (three
+fluctuations for the last window, which lies past the decorrelation time: see the comment at the assertion).
 """
 import numpy as np
 import pytest
@@ -72,10 +73,15 @@ def test_energy_and_momentum_drift_match_the_oracle(oracle_curves, kernel):
         bound = max(20 * env[t - 1], floor)
         assert rel[t - 1] <= bound, f"KE drift at step {t}: {rel[t-1]:.3e} > {bound:.3e} (oracle envelope {env[t-1]:.3e})"
         assert prel[t - 1] <= bound, f"momentum drift at step {t}: {prel[t-1]:.3e} > {bound:.3e}"
-    # time-averaged energy per 100-step window agrees within the window's own fluctuation
+    # time-averaged energy per 100-step window agrees within the window's own fluctuation.  The pair kernel adds
+    # forces with floating-point atomics, so two runs of the SAME binary differ in summation order and decorrelate
+    # like any other pair of implementations: over 16 repeated runs the first three windows agreed with the oracle
+    # to < 0.005 fluctuations, the last one (steps 300-400, past the decorrelation time) scattered between 0.17
+    # and 1.2 fluctuations — hence three fluctuations there.
     for a in range(0, STEPS, 100):
         m_gpu, m_ref, s_ref = ke[a:a + 100].mean(), ke_ref[a:a + 100].mean(), ke_ref[a:a + 100].std()
-        assert abs(m_gpu - m_ref) <= max(s_ref, 0.02 * m_ref), (a, m_gpu, m_ref, s_ref)
+        slack = 3.0 if a >= 300 else 1.0
+        assert abs(m_gpu - m_ref) <= slack * max(s_ref, 0.02 * m_ref), (a, m_gpu, m_ref, s_ref)
     print(f"\nkernel {kernel}: KE rel diff at 10/50/100/200/400 = "
           + ", ".join(f"{rel[t-1]:.2e}" for t in (10, 50, 100, 200, 400))
           + " | oracle f32-vs-f64 envelope = " + ", ".join(f"{env[t-1]:.2e}" for t in (10, 50, 100, 200, 400)))

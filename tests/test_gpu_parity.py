@@ -241,6 +241,30 @@ def test_errors_match_reference_panics(eng, default_params):
                    _abi.FORCE_AUTO)
 
 
+def test_device_side_type_sort_edge_cases(eng, default_params):
+    """The type-grouped layout is a device-side stable counting sort (k_type_hist / k_type_scan /
+    k_pack_typed): absent types, one dominant type, counts straddling the 256-particle CTA of the sort,
+    and the first offending index in the error of src/lib.rs:225-228."""
+    rng = np.random.default_rng(5)
+    T = 7
+    A = rng.uniform(-1, 1, T * T).astype(np.float32)
+    prm = dict(default_params, id_count=T, attraction_matrix=list(A), world_size=9.0)
+    for n, ids in ((1, [6]), (257, [0, 6]), (5000, [3]), (5000, [0, 6]), (4097, [1, 2, 5])):
+        start = p3.generate_particles(9.0, n, seed=n, id_count=T)
+        start["id"] = rng.choice(ids, n).astype(np.uint32)
+        if n == 5000 and ids == [3]:
+            start["id"][::997] = 5  # a handful of another type inside one dominant type
+        ref = O.update(prm, TS, start, mode=O.IDEAL)["out"]
+        for block in (128, 256):
+            assert_parity(gpu_update(eng, prm, start, _abi.FORCE_PAIR, block=block), ref, 9.0, what=f"n={n} ids={ids} B={block}")
+    bad = p3.generate_particles(9.0, 3000, seed=1, id_count=T)
+    bad["id"][[2999, 1234, 2000]] = (7, 9, 4000000000)
+    with pytest.raises(IndexError, match="particle 1234 has id 9"):
+        gpu_update(eng, prm, bad, _abi.FORCE_PAIR)
+    good = p3.generate_particles(9.0, 3000, seed=1, id_count=T)  # the engine stays usable after the error
+    assert_parity(gpu_update(eng, prm, good, _abi.FORCE_PAIR), O.update(prm, TS, good, mode=O.IDEAL)["out"], 9.0)
+
+
 def test_particles_update_semantics(default_params):
     """past_particles = pre-step state, active = post-step, return value is a copy; N and every
     parameter may change between calls (src/lib.rs:167-171,268-271; main.rs:263-359)."""
