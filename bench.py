@@ -454,6 +454,33 @@ def run_engine(args):
                        "d2h_bytes_per_step": n * 28, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                        "api": "per rank: p3d_upload + sharded step + p3d_download on pinned host arrays"}
 
+    # ---------------- multi-GPU: where a step's time goes on every rank (diagnostic, outside the timed region) ----------------
+    if world > 1 and fused:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        acc = [0.0, 0.0, 0.0]
+        d_steps = 3
+        for _ in range(d_steps):
+            barrier()
+            evs[0].record(stream)
+            eng.shard_force(P)                      # partition + this rank's block rows (pair + boundary kernels)
+            evs[1].record(stream)
+            dist.all_reduce(stepper._bar)           # waits for the slowest rank's force pass
+            evs[2].record(stream)
+            eng.shard_integrate_fused(P, TS)        # P2P reduce-scatter + integrate + all-gather
+            dist.all_reduce(stepper._bar)
+            evs[3].record(stream)
+            eng.shard_commit()
+            torch.cuda.synchronize()
+            for k in range(3):
+                acc[k] += evs[k].elapsed_time(evs[k + 1]) / d_steps
+        allp = [None] * world
+        dist.all_gather_object(allp, acc)
+        line["phases_ms_per_rank"] = {
+            "what": "3 untimed diagnostic steps, CUDA events on each rank: own force pass | waiting for the slowest rank "
+                    "(first barrier) | fused P2P integrate + second barrier",
+            "force": [round(a[0], 3) for a in allp], "wait_for_slowest": [round(a[1], 3) for a in allp],
+            "exchange_integrate": [round(a[2], 3) for a in allp]}
+
     # ---------------- the other cloud (north_star: uniform AND clustered clouds at every GPU count) ----------------
     if not args.no_other_cloud and n >= 4096:
         other = "plummer" if args.cloud == "uniform" else "uniform"
