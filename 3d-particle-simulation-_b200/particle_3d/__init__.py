@@ -104,6 +104,12 @@ class Engine:
         _abi.check(self._lib.p3d_download(self._h, out.ctypes.data, self._n))
         return out
 
+    def download_into(self, out: np.ndarray):
+        """p3d_download into a caller-owned (e.g. pinned) buffer of self._n particles."""
+        if out.dtype != PARTICLE or out.shape[0] != self._n or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"out must be a contiguous PARTICLE array of {self._n} entries")
+        _abi.check(self._lib.p3d_download(self._h, out.ctypes.data, self._n))
+
     def download_forces(self) -> np.ndarray:
         out = np.zeros((self._n, 3), dtype=np.float32)
         _abi.check(self._lib.p3d_download_forces(self._h, out.ctypes.data, self._n))

@@ -436,7 +436,9 @@ def run_engine(args):
         # multi-GPU e2e: every step uploads the full state from pinned host memory on every rank and
         # reads the rank's shard back (the host mirror would do exactly this per update()).
         hin = torch.empty(n * 28, dtype=torch.uint8).pin_memory()
+        hout = torch.empty(n * 28, dtype=torch.uint8).pin_memory()
         a_in = hin.numpy().view(_abi.PARTICLE)
+        a_out = hout.numpy().view(_abi.PARTICLE)
         a_in[:] = parts
         barrier()
         t0 = time.perf_counter()
@@ -444,7 +446,7 @@ def run_engine(args):
             eng.upload(a_in, prm["id_count"])  # same-size re-upload: device buffers (and IPC mappings) stay put
             stepper.reset()
             stepper.step(P, TS, 1)
-            out = eng.download()
+            eng.download_into(a_out)
         barrier()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
         tt = torch.tensor([e2e_s], device=f"cuda:{local}")

@@ -548,6 +548,11 @@ def test_options_round_trip_and_timing(default_params):
         ref = O.update(prm, TS, ref, mode=O.IDEAL)["out"]
     dv, dp = parity_errors(out, ref, W)
     assert dv.max() < 5e-5 and dp.max() < 5e-5
+    into = np.empty(8000, _abi.PARTICLE)
+    e.download_into(into)                # caller-owned buffer: same bytes as the allocating form
+    assert into.tobytes() == out.tobytes()
+    with pytest.raises(ValueError):
+        e.download_into(np.empty(7999, _abi.PARTICLE))
     with pytest.raises(p3.P3DError):  # id_count must match the uploaded layout
         e.step(p3.Engine.make_params(**dict(prm, id_count=4, attraction_matrix=[0.0] * 16)), TS, 1)
     e.close()
