@@ -292,11 +292,14 @@ def run_engine(args):
     for _ in range(args.warmup):
         one_step()
         flush.zero_()
-    barrier()
     c0 = eng.counters()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern = {"force": 0.0, "pair": 0.0, "bxb": 0.0, "integrate": 0.0, "partition": 0.0, "steps": 0}
     with ClockSampler(local) as clocks:
+        # the sampler starts (nvmlInit: milliseconds, different on every rank) BEFORE the barrier, so that all ranks
+        # enter the timed region together; its samples from before the barrier are dropped
+        barrier()
+        clocks.rows.clear()
         ev0.record(stream)
         for _ in range(args.steps):
             one_step()
