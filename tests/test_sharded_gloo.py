@@ -101,6 +101,12 @@ def _worker(rank, world, port, n, steps, outdir):
     np.save(os.path.join(outdir, f"pos_{rank}.npy"), eng.pos[eng.cur].numpy()[:n, :3])
     np.save(os.path.join(outdir, f"vel_{rank}.npy"), eng.vel[:n])
     np.save(os.path.join(outdir, f"rng_{rank}.npy"), np.array([s0, s1, st.collectives]))
+    # a re-upload puts the engine back on its first position buffer: after an odd number of steps the stepper's
+    # cached buffer views are for the other parity and reset() must drop them
+    eng.__init__(prm, parts, rank, world)
+    st.reset()
+    st.step(None, TS, 2)
+    np.save(os.path.join(outdir, f"pos2_{rank}.npy"), eng.pos[eng.cur].numpy()[:n, :3])
     dist.destroy_process_group()
 
 
@@ -126,6 +132,11 @@ def test_sharded_stepper_over_gloo(tmp_path, world):
         assert np.array_equal(vel[s0:e], refv[s0:e])  # velocities live on the owning rank
         covered[s0:e] = True
     assert covered.all()
+    ref2 = p3.generate_particles(12.0, n, seed=4)
+    for _ in range(2):
+        ref2 = O.update(prm, TS, ref2, mode=O.IDEAL)["out"]
+    for r in range(world):  # the run after re-upload + reset()
+        assert np.array_equal(np.load(tmp_path / f"pos2_{r}.npy"), np.stack([ref2["px"], ref2["py"], ref2["pz"]], 1))
 
 
 def test_shard_arithmetic():
