@@ -29,5 +29,31 @@ struct DevParams {
     float reach;  // min(r, max(1, m)): beyond this distance the force is exactly zero
 };
 
+// Optional self-checking build (-DP3D_BOUNDS_CHECK; compute-sanitizer is not available on the target pool):
+// every data-dependent slot / cell index is compared with the extent the engine published before the
+// launch; a violation is counted and the access skipped.  Compiles to nothing in the product build.
+#ifdef P3D_BOUNDS_CHECK
+static __device__ unsigned int g_p3d_slots, g_p3d_cells;
+static __device__ unsigned long long g_p3d_oob;
+__device__ __forceinline__ bool p3d_in_range(unsigned long long i, unsigned long long n) {
+    if (i < n) return true;
+    atomicAdd(&g_p3d_oob, 1ull);
+    return false;
+}
+// extents are published by a kernel (by-value arguments survive CUDA-graph capture; a memcpy from a host
+// variable would be replayed from a dangling pointer); 0xFFFFFFFF leaves a value as it is
+__global__ void k_debug_publish(unsigned int slots, unsigned int cells) {
+    if (slots != 0xFFFFFFFFu) g_p3d_slots = slots;
+    if (cells != 0xFFFFFFFFu) g_p3d_cells = cells;
+}
+#define P3D_SLOT_OK(s) p3d_in_range((unsigned long long)(s), (unsigned long long)g_p3d_slots)
+#define P3D_SLOT_END_OK(s) p3d_in_range((unsigned long long)(s), (unsigned long long)g_p3d_slots + 1ull)
+#define P3D_CELL_OK(c) p3d_in_range((unsigned long long)(c), (unsigned long long)g_p3d_cells + 1ull)
+#else
+#define P3D_SLOT_OK(s) true
+#define P3D_SLOT_END_OK(s) true
+#define P3D_CELL_OK(c) true
+#endif
+
 __device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }

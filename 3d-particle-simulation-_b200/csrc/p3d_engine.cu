@@ -307,6 +307,9 @@ int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T, bo
 int launch_pack(p3d_engine *e, size_t n) {
     cudaStream_t st = e->stream;
     const int ns = e->n_slots;
+#ifdef P3D_BOUNDS_CHECK
+    k_debug_publish<<<1, 1, 0, st>>>((unsigned int)ns, 0xFFFFFFFFu);
+#endif
     e->cur = 0;
     e->parity = 0;
     k_fill_ghosts<<<(ns + 255) / 256, 256, 0, st>>>(e->pos[0].p, e->pos[1].p, e->vel.p, e->frc.p, ns);
@@ -368,6 +371,9 @@ int build_cells(p3d_engine *e, const DevParams &P, const float4 *pos, int *flag_
     }
     if ((rc = e->cpos.ensure((size_t)ns))) return rc;
     if ((rc = e->cell_off.ensure(ncell + 2))) return rc;
+#ifdef P3D_BOUNDS_CHECK
+    k_debug_publish<<<1, 1, 0, st>>>(0xFFFFFFFFu, (unsigned int)ncell);
+#endif
     int end_bit = 1;
     while ((1ull << end_bit) <= ncell) ++end_bit;
     size_t tmp_bytes = 0;
@@ -723,6 +729,18 @@ int run_steps(p3d_engine *e, const p3d_params *prm, const DevParams &P, float ts
 extern "C" {
 
 int p3d_abi_version(void) { return P3D_ABI_VERSION; }
+
+int p3d_debug_bounds_violations(p3d_engine *e, unsigned long long *count) {
+    if (!e || !count) return fail(P3D_ERR_INVALID, "null argument");
+#ifdef P3D_BOUNDS_CHECK
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpyFromSymbol(count, g_p3d_oob, sizeof(unsigned long long)));
+#else
+    *count = ~0ull;  // not a self-checking build
+#endif
+    return P3D_OK;
+}
 
 const char *p3d_last_error(void) { return g_last_error.c_str(); }
 

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(kTypeThreads) k_pack_typed(const float *__rest
     uint32_t before = 0u;
     for (int w = 0; w < warp; ++w) before += wcnt[w][id];
     const uint32_t s = (uint32_t)seg_start[id] + cta_off[(size_t)blockIdx.x * id_count + id] + before + (uint32_t)rank;
+    if (!P3D_SLOT_OK(s)) return;
     pos[s] = make_float4(p[0], p[1], p[2], p[6]);  // w carries the id bits
     vel[s] = make_float4(p[3], p[4], p[5], 0.f);
     slot_of[base + t] = s;
@@ -152,7 +153,8 @@ __global__ void __launch_bounds__(256) k_unpack(const float4 *__restrict__ pos, 
     const int cnt = min(256, n - base);
     const int t = threadIdx.x;
     if (t < cnt) {
-        const uint32_t s = slot_of ? slot_of[base + t] : (uint32_t)(base + t);
+        uint32_t s = slot_of ? slot_of[base + t] : (uint32_t)(base + t);
+        if (!P3D_SLOT_OK(s)) s = 0u;  // (self-checking build only)
         const float4 p = pos[s];
         const float4 v = vel[s];
         float *o = sm + t * 7;
@@ -174,6 +176,7 @@ __global__ void __launch_bounds__(256) k_unpack_render(const float4 *__restrict_
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t s = slot_of ? slot_of[i] : (uint32_t)i;
+    if (!P3D_SLOT_OK(s)) return;
     const float4 p = pos[s];
     const float4 v = vel[s];
     out[2 * i] = make_float4(p.x, p.y, p.z, 0.0f);
@@ -186,7 +189,9 @@ __global__ void __launch_bounds__(256) k_unpack_forces(const float4 *__restrict_
                                                        float *__restrict__ out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 f = frc[slot_of ? slot_of[i] : (uint32_t)i];
+    const uint32_t s = slot_of ? slot_of[i] : (uint32_t)i;
+    if (!P3D_SLOT_OK(s)) return;
+    const float4 f = frc[s];
     out[3 * i] = f.x; out[3 * i + 1] = f.y; out[3 * i + 2] = f.z;
 }
 

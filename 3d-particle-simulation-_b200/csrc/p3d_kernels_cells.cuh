@@ -63,11 +63,13 @@ __global__ void __launch_bounds__(256) k_cell_gather(const float4 *__restrict__ 
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_slots) return;
     const uint32_t key = keys_sorted[k];
-    cpos[k] = pos[vals_sorted[k]];
+    if (P3D_SLOT_OK(vals_sorted[k])) cpos[k] = pos[vals_sorted[k]];
     const uint32_t first = (k == 0) ? 0u : keys_sorted[k - 1] + 1u;
-    for (uint32_t c = first; c <= key; ++c) cell_off[c] = (uint32_t)k;  // no iterations when the key repeats
+    for (uint32_t c = first; c <= key; ++c)
+        if (P3D_CELL_OK(c)) cell_off[c] = (uint32_t)k;  // no iterations when the key repeats
     if (k == n_slots - 1)
-        for (uint32_t c = key + 1u; c <= n_cells; ++c) cell_off[c] = (uint32_t)n_slots;
+        for (uint32_t c = key + 1u; c <= n_cells; ++c)
+            if (P3D_CELL_OK(c)) cell_off[c] = (uint32_t)n_slots;
 }
 
 // One candidate of the cell list: the reference's relative position (src/lib.rs:211-212) and the
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(kCellThreads) k_force_cells(const float4 *__re
             if (++run >= n_runs) goto done;
             j = run_lo[run][t];
             hi = run_hi[run][t];
+            if (!P3D_SLOT_END_OK(hi)) hi = j;  // (self-checking build only)
             const int img = run_img[run][t];
             const int ix = img & 3, iy = (img >> 2) & 3, iz = (img >> 4) & 3;
             px = ix == 0 ? sx3[0] : (ix == 1 ? sx3[1] : sx3[2]);
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(kCellThreads) k_force_cells(const float4 *__re
         ++j;
     }
 done:
-    frc[vals_sorted[k]] = make_float4(ax, ay, az, 0.f);
+    if (P3D_SLOT_OK(vals_sorted[k])) frc[vals_sorted[k]] = make_float4(ax, ay, az, 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(128) k_quirk_correction(const float4 *__restri
                 float px = pi.x;
                 if (nx < 0) { nx += nc; px = pxp; } else if (nx >= nc) { nx -= nc; px = pxm; }
                 const uint32_t c = (uint32_t)((nz * nc + ny) * nc + nx);
-                const uint32_t s0 = cell_off[c], s1 = cell_off[c + 1];
+                const uint32_t s0 = cell_off[c], s1 = P3D_SLOT_END_OK(cell_off[c + 1]) ? cell_off[c + 1] : s0;
                 for (uint32_t j = s0; j < s1; ++j) {
                     const float4 q = cpos[j];
                     const float rx = __fsub_rn(q.x, px), ry = __fsub_rn(q.y, py), rz = __fsub_rn(q.z, pz);
@@ -318,5 +321,5 @@ __global__ void __launch_bounds__(128) k_quirk_correction(const float4 *__restri
             }
         }
     }
-    if (any) atomicAdd(frc + vals_sorted[k], make_float4(ax, ay, az, 0.0f));
+    if (any && P3D_SLOT_OK(vals_sorted[k])) atomicAdd(frc + vals_sorted[k], make_float4(ax, ay, az, 0.0f));
 }

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(
     int dst = -1;
     if (interior) dst = seg_start[t] + off.x + wi + __popc(mi & lt);
     else if (boundary) dst = seg_end[t] - 1 - (off.y + wb + __popc(mb & lt));
-    if (dst >= 0) {
+    if (dst >= 0 && P3D_SLOT_OK(dst)) {
         spos[dst] = p;
         sx[dst] = p.x; sy[dst] = p.y; sz[dst] = p.z;
         sidx[dst] = (uint32_t)s;
@@ -343,15 +343,15 @@ k_force_pair(const float *__restrict__ sx, const float *__restrict__ sy, const f
             // 32 rotations bring every j (and its accumulator) back to its home lane
             if (!diag) {
                 const uint32_t s0 = sidx[base], s1 = sidx[base + 1];
-                if (s0 != P3D_GHOST_ID) atomic_add_f3(frc + s0, -ajx.x, -ajy.x, -ajz.x);
-                if (s1 != P3D_GHOST_ID) atomic_add_f3(frc + s1, -ajx.y, -ajy.y, -ajz.y);
+                if (s0 != P3D_GHOST_ID && P3D_SLOT_OK(s0)) atomic_add_f3(frc + s0, -ajx.x, -ajy.x, -ajz.x);
+                if (s1 != P3D_GHOST_ID && P3D_SLOT_OK(s1)) atomic_add_f3(frc + s1, -ajx.y, -ajy.y, -ajz.y);
             }
         }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const uint32_t s = sidx[row * B + r * 32 + lane];
-        if (s != P3D_GHOST_ID)
+        if (s != P3D_GHOST_ID && P3D_SLOT_OK(s))
             atomic_add_f3(frc + s, aix[r].x + aix[r].y, aiy[r].x + aiy[r].y, aiz[r].x + aiz[r].y);
     }
 }
@@ -451,5 +451,5 @@ __global__ void __launch_bounds__(B) k_force_bxb(const float4 *__restrict__ spos
             }
         }
     }
-    if (live) atomic_add_f3(frc + sidx[row * B + threadIdx.x], ax, ay, az);
+    if (live && P3D_SLOT_OK(sidx[row * B + threadIdx.x])) atomic_add_f3(frc + sidx[row * B + threadIdx.x], ax, ay, az);
 }

@@ -126,6 +126,12 @@ class Engine:
         _abi.check(self._lib.p3d_diagnostics(self._h, d))
         return {"ke": d[0], "p": (d[1], d[2], d[3]), "max_v2": d[4], "count": int(d[5]), "sum_p2": d[6]}
 
+    def debug_bounds_violations(self):
+        """Out-of-range slot / cell indices caught by a self-checking build (-DP3D_BOUNDS_CHECK); None for a product build."""
+        c = C.c_ulonglong(0)
+        _abi.check(self._lib.p3d_debug_bounds_violations(self._h, C.byref(c)))
+        return None if c.value == 2 ** 64 - 1 else int(c.value)
+
     def set_option(self, option: int, value: int):
         _abi.check(self._lib.p3d_set_option(self._h, option, value))
 

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_ROOT, "libp3d.so")
+# P3D_LIB: load another build of the same library instead (the self-checking build of tests/test_gpu_bounds.py)
+LIB_PATH = os.environ.get("P3D_LIB") or os.path.join(_PKG_ROOT, "libp3d.so")
 
 # error codes (include/p3d.h)
 OK, ERR_WORLD_TOO_SMALL, ERR_BAD_ID, ERR_CUDA, ERR_INVALID, ERR_NO_DEVICE = 0, 1, 2, 3, 4, 5
@@ -52,6 +53,7 @@ EXPORTS = [
     "p3d_shard_range", "p3d_shard_force", "p3d_shard_integrate", "p3d_shard_commit",
     "p3d_ipc_export", "p3d_ipc_import", "p3d_ipc_close", "p3d_shard_integrate_fused",
     "p3d_scene_default_params", "p3d_scene_uniform", "p3d_scene_plummer", "p3d_microbench",
+    "p3d_debug_bounds_violations",
 ]
 
 _lib = None
@@ -129,6 +131,8 @@ def load():
     L.p3d_scene_plummer.argtypes = [C.c_uint64, sz, f32, f32, C.c_uint32, vp]
     L.p3d_microbench.restype = i32
     L.p3d_microbench.argtypes = [i32, i32, i32, C.POINTER(C.c_double)]
+    L.p3d_debug_bounds_violations.restype = i32
+    L.p3d_debug_bounds_violations.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     _lib = L
     return L
 

@@ -165,6 +165,11 @@ int p3d_shard_integrate_fused(p3d_engine *eng, const p3d_params *prm, float ts);
  * out[0] = FP32 lane-FMAs per second (an FFMA2 counts 2 per lane), out[1] = kernel ms,
  * out[2] = SM count, out[3] = max SM clock in MHz as reported by the driver. */
 int p3d_microbench(int device, int kind, int iters, double out[4]);
+/* Self-checking builds (-DP3D_BOUNDS_CHECK: every data-dependent slot / cell index in the kernels is compared
+ * with its extent, violations are counted and the access skipped): number of violations since the library was
+ * loaded.  A product build stores UINT64_MAX.  (No reference counterpart: Rust's slice indexing panics,
+ * src/lib.rs:225-228; compute-sanitizer is unavailable on the target pool.) */
+int p3d_debug_bounds_violations(p3d_engine *eng, unsigned long long *count);
 
 /* ---- seeded scenes (host only; restates the binary-private generator, src/bin/main.rs:60-87,
  *      and the default scene constants, src/bin/main.rs:123-148) ---- */
