@@ -4,6 +4,7 @@ the file bench.py reads for `roofline.traffic` and `roofline.ncu`.  Not part of 
   ncu -i gpurun_out/r01_force_pair_n1m.ncu-rep --page raw --csv > profiles/r01_kernels_n1048576_raw.csv
   ncu -i gpurun_out/r01_kernels_n262144.ncu-rep --page raw --csv > profiles/r01_kernels_n262144_raw.csv
   ncu -i gpurun_out/r01_cells_n1m.ncu-rep        --page raw --csv > profiles/r01_cells_n1048576_raw.csv
+  ncu -i gpurun_out/r01_layout_n1m.ncu-rep       --page raw --csv > profiles/r01_layout_n1048576_raw.csv
   python tools/ncu_summary.py
 """
 import csv
@@ -53,7 +54,8 @@ def main():
     summary = {"source": f"profiles/{main_csv} (ncu --set full --clock-control none --import-source on, one launch, N=1,048,576)",
                "n_particles": 1048576}
     summary.update(top)
-    for key, name in (("other_kernels_n262144", "r01_kernels_n262144_raw.csv"), ("cell_list_kernels_n1048576", "r01_cells_n1048576_raw.csv")):
+    for key, name in (("other_kernels_n262144", "r01_kernels_n262144_raw.csv"), ("cell_list_kernels_n1048576", "r01_cells_n1048576_raw.csv"),
+                      ("layout_kernels_n1048576", "r01_layout_n1048576_raw.csv")):
         p = os.path.join(PROF, name)
         if os.path.exists(p):
             summary[key] = {"source": f"profiles/{name}", "kernels": kernels(p)}
