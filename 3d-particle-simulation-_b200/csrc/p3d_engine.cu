@@ -518,7 +518,8 @@ int launch_force(p3d_engine *e, const DevParams &P) {
     const int rows = (M - e->rank + e->world - 1) / e->world;  // rows rank, rank+world, ...
     if (rows > 0) {
         // One warp per CTA: every per-block-pair scalar is then provably warp-uniform and lives in
-        // uniform registers (no register-file reads in the FFMA2 stream).  ~128 waves of 16 CTAs/SM
+        // uniform registers (no register-file reads in the FFMA2 stream).  About 2048 CTAs per SM
+        // (~170 waves of the 12 resident one-warp CTAs of the R = 8 kernel, ~128 waves of the 16 of the R = 4 kernel)
         // keep the tail of the last wave small; never more warps than offsets in a row.
         const int offsets = M / 2 + 1;
         int splits = (int)std::min<long long>(offsets, std::max<long long>(1, (128LL * 16 * e->sm_count + rows - 1) / rows));
