@@ -333,10 +333,12 @@ def run_engine(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "force_kernel": "k_force_pair: all N^2 pairs (north_star); the cell list is reported separately",
         "config": config_dict(n, W, {"parallelism": (f"block rows sharded over {world} GPUs; " + ("per step ONE fused kernel does reduce-scatter(forces) + integrate + all-gather(positions) over NVLink peer memory, NCCL only as two 4-byte barrier all-reduces" if fused else "per step all-reduce(forces) + all-gather(positions) over NCCL")) if world > 1 else "1 GPU",
-                                     "block": args.block}, cloud=args.cloud),
+                                     "block": args.block,
+                                     **({"weak_scaling": "N = 1,048,576 * sqrt(GPUs) (BASELINE.json configs[4]): the pair count per GPU is that of the 1-GPU run"} if args.weak else {})},
+                                    cloud=args.cloud),
         "steps_per_s": 1e3 / ms_per_step,
         "gpu_launches": int(launches),
         "clocks": clock_summary,
@@ -616,7 +618,14 @@ def main():
     ap.add_argument("--cloud", default="uniform", choices=["uniform", "plummer"],
                     help="cloud the headline numbers are measured on (the other one is reported in `other_cloud`)")
     ap.add_argument("--no-other-cloud", action="store_true", help="skip the `other_cloud` section")
+    ap.add_argument("--weak", action="store_true",
+                    help="weak scaling (BASELINE.json config 5): N = 1,048,576 * sqrt(gpus), so that the pair count per GPU "
+                         "stays that of the 1-GPU run; density 1")
     args = ap.parse_args()
+    if args.weak:
+        unit = 256 * max(1, args.gpus)
+        args.n = int(round(N_DEFAULT * (max(1, args.gpus) ** 0.5) / unit)) * unit
+        args.world_size = None if args.gpus == 1 else round(float(args.n) ** (1.0 / 3.0), 1)
     if args.world_size is None:
         args.world_size = W_DEFAULT if args.n == N_DEFAULT else round(float(args.n) ** (1.0 / 3.0), 1)
     if args.warmup < 3:
