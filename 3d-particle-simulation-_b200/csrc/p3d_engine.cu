@@ -47,6 +47,7 @@ int fail(int code, const char *fmt, ...) {
 constexpr int kMaxTimedSteps = 512;
 constexpr int kEv = 5;  // events per timed step
 constexpr int kRefTile = 128;       // threads per CTA of the reference-order kernel
+constexpr int kOutOfBoxCellsMin = 32768;  // all-pairs path, out-of-box input, single-step call: cell list from this n
 constexpr int kCellsAutoMin = 192;  // P3D_FORCE_AUTO uses the cell list from this n (its ~12 launches cost ~35 us),
                                     // the single-launch reference-order kernel below
 
@@ -116,6 +117,7 @@ struct p3d_engine {
     int opt_block_sort = 1;
     int opt_faithful = 0;    // K5: add the reference's bucket double-visit contributions
     int opt_graph = 1;       // replay device-resident multi-step runs through a CUDA graph (two steps per graph)
+    int force_override = -1; // >= 0: force kernel for the steps of the current call (see run_steps)
 
     // CUDA graph of two consecutive steps (returns cur/parity to their starting values)
     cudaGraphExec_t graph_exec = nullptr;
@@ -343,7 +345,9 @@ int resolve_force_kernel_for(const p3d_engine *e, size_t n) {
     if (e->opt_force == P3D_FORCE_AUTO) return n >= (size_t)kCellsAutoMin ? P3D_FORCE_CELLS : P3D_FORCE_REFERENCE_ORDER;
     return e->opt_force;
 }
-int resolve_force_kernel(const p3d_engine *e) { return resolve_force_kernel_for(e, e->n); }
+int resolve_force_kernel(const p3d_engine *e) {
+    return e->force_override >= 0 ? e->force_override : resolve_force_kernel_for(e, e->n);
+}
 
 size_t ref_smem(int tile, int T) { return (size_t)tile * sizeof(float4) + (size_t)T * T * sizeof(float); }
 
@@ -699,6 +703,19 @@ int run_steps(p3d_engine *e, const p3d_params *prm, const DevParams &P, float ts
     int rc;
     if ((rc = upload_matrix(e, prm))) return rc;
     if ((rc = check_box_now(e, P))) return rc;  // world_size may have changed since the last call
+    // All-pairs kernel with a particle outside the box: on the device the exact O(27 N^2) reference-order kernel
+    // takes such a step over, which is minutes at N = 1M.  A single-step call (p3d_update) can afford to look at
+    // the flag: the cell list's general variant evaluates the same images in O(N), whatever the layout.
+    struct OverrideGuard {
+        p3d_engine *e;
+        ~OverrideGuard() { e->force_override = -1; }
+    } guard{e};
+    if (n_steps == 1 && e->world == 1 && e->n >= (size_t)kOutOfBoxCellsMin && resolve_force_kernel(e) == P3D_FORCE_PAIR) {
+        int outside = 0;
+        CU(cudaMemcpyAsync(&outside, e->flags.p + e->parity, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        if (outside) e->force_override = P3D_FORCE_CELLS;
+    }
     e->timed_steps = 0;
     if (e->opt_timing && (rc = ensure_events(e, n_steps))) return rc;
     int s = 0;

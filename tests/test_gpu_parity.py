@@ -188,6 +188,28 @@ def test_positions_outside_the_box(eng, default_params, kernel):
     assert_parity(gpu_update(eng, default_params, start, kernel), ref, 10.0)
 
 
+def test_all_pairs_update_with_outside_positions_at_large_n(eng, default_params):
+    """p3d_update with the all-pairs kernel and a particle outside the box: from 32,768 particles the single-step
+    call hands that step to the cell list's general variant (same images, O(N)) instead of the exact O(27 N^2)
+    kernel, on the type-grouped layout; the force-kernel option itself is untouched."""
+    import time
+    W, n = 34.2, 40000
+    prm = dict(default_params, world_size=W)
+    start = p3.generate_particles(W, n, seed=8)
+    start["px"][::7] += W
+    start["py"][::11] -= W
+    start["pz"][::13] += 2.3 * W  # beyond every image
+    ref = O.update(prm, TS, start, mode=O.IDEAL)["out"]
+    out = gpu_update(eng, prm, start, _abi.FORCE_PAIR)
+    assert_parity(out, ref, W)
+    assert eng.get_option(_abi.OPT_FORCE_KERNEL) == _abi.FORCE_PAIR
+    t0 = time.perf_counter()
+    gpu_update(eng, prm, start, _abi.FORCE_PAIR)
+    assert time.perf_counter() - t0 < 0.05  # the O(27 N^2) kernel needs ~0.1 s here
+    inside = p3.generate_particles(W, n, seed=8)  # and the next in-box call is the pair kernel again
+    assert_parity(gpu_update(eng, prm, inside, _abi.FORCE_PAIR), O.update(prm, TS, inside, mode=O.IDEAL)["out"], W)
+
+
 @pytest.mark.parametrize("kernel", KERNELS, ids=IDS)
 def test_fast_particle_single_wrap(eng, default_params, kernel):
     start = p3.generate_particles(10.0, 600, seed=8)
