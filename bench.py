@@ -137,6 +137,14 @@ class ClockSampler:
                         "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows), "source": "nvidia-smi -lms 100"}
 
 
+def weak_particles(gpus: int) -> int:
+    """BASELINE.json config 5, weak scaling: the all-pairs work per GPU, N^2 / G, is held at the 1-GPU value, so
+    N_G = 1,048,576 * sqrt(G), rounded to a whole number of 256-particle blocks per GPU."""
+    g = max(1, int(gpus))
+    unit = 256 * g
+    return int(round(N_DEFAULT * (g ** 0.5) / unit)) * unit
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -623,8 +631,7 @@ def main():
                          "stays that of the 1-GPU run; density 1")
     args = ap.parse_args()
     if args.weak:
-        unit = 256 * max(1, args.gpus)
-        args.n = int(round(N_DEFAULT * (max(1, args.gpus) ** 0.5) / unit)) * unit
+        args.n = weak_particles(args.gpus)
         args.world_size = None if args.gpus == 1 else round(float(args.n) ** (1.0 / 3.0), 1)
     if args.world_size is None:
         args.world_size = W_DEFAULT if args.n == N_DEFAULT else round(float(args.n) ** (1.0 / 3.0), 1)

@@ -56,3 +56,16 @@ def test_graft_entry_points_exist():
     import __graft_entry__ as g
 
     assert callable(g.build) and callable(g.smoke)
+
+
+def test_weak_scaling_particle_counts():
+    """--weak holds the all-pairs work per GPU at the 1-GPU value: N_G = 1,048,576 * sqrt(G), whole blocks per GPU."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert bench.weak_particles(1) == 1048576
+    for g in (2, 4, 8):
+        n = bench.weak_particles(g)
+        assert n % (256 * g) == 0
+        assert abs(n * n / g / 1048576.0 ** 2 - 1.0) < 2e-3
+    assert bench.weak_particles(8) == 2965504  # the run recorded in DESIGN.md
