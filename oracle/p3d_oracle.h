@@ -10,7 +10,9 @@
  * reference binary cannot be run.  The oracle is pinned instead by (i) SipHash
  * known-answer vectors from the SipHash paper, (ii) hand-derived known answers for
  * every helper, (iii) an independent brute-force f64 all-pairs
- * evaluation over the 27 periodic images which must agree with the cell-list walk.
+ * evaluation over the 27 periodic images which must agree with the cell-list walk,
+ * (iv) a second restatement written separately in Python (oracle/lib_rs_twin.py) that must
+ * agree with this file's faithful mode bit for bit (tests/test_oracle_twin.py).
  */
 #ifndef P3D_ORACLE_H
 #define P3D_ORACLE_H
