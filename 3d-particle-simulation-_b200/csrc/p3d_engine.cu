@@ -198,6 +198,15 @@ int ensure_common(p3d_engine *e, size_t n, size_t ns) {
 
 int resolve_force_kernel_for(const p3d_engine *e, size_t n);
 
+// A sharded engine computes PARTIAL forces (its block rows) and integrates only its slot range; between the two
+// the driver has to sum the forces and afterwards gather the positions.  A whole-step call would silently
+// integrate with partial forces, so it is refused.
+int fail_sharded(const p3d_engine *e, const char *call) {
+    return fail(P3D_ERR_INVALID, "%s on a sharded engine (rank %d of %d): a whole step needs the driver's collectives - use "
+                "p3d_shard_force / p3d_shard_integrate[_fused] / p3d_shard_commit, or p3d_set_shard(eng, 0, 1) first",
+                call, e->rank, e->world);
+}
+
 // Identity layout (slot = caller index): all the cell-list and reference-order kernels need.  No host
 // pass over the particles; ids are validated on the device by k_pack.
 int build_layout_identity(p3d_engine *e, size_t n, uint32_t T) {
@@ -779,14 +788,21 @@ int p3d_create(int device, p3d_engine **out) {
                     prop.minor);
     cudaStream_t stream = nullptr, aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     int prio_lo = 0, prio_hi = 0;
-    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    // highest priority: its few CTAs are placed as soon as slots free up, instead of queueing behind the
-    // tens of thousands of pair-kernel CTAs
-    CU(cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, prio_hi));
-    CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    // highest priority for the auxiliary stream: its few CTAs are placed as soon as slots free up, instead of
+    // queueing behind the tens of thousands of pair-kernel CTAs
+    cudaError_t ce = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, prio_hi);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+    if (ce != cudaSuccess) {  // nothing half-made is left behind
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (aux) cudaStreamDestroy(aux);
+        if (stream) cudaStreamDestroy(stream);
+        return fail(P3D_ERR_CUDA, "creating the engine's streams/events failed: %s", cudaGetErrorString(ce));
+    }
     p3d_engine *e = new p3d_engine();
     e->aux_stream = aux;
     e->ev_fork = ev_fork;
@@ -910,6 +926,7 @@ int p3d_step(p3d_engine *e, const p3d_params *prm, float ts, int n_steps) {
         return fail(P3D_ERR_INVALID, "id_count %u differs from the uploaded layout (%u): upload again", prm->id_count,
                     e->T);
     if (e->n_slots == 0) return fail(P3D_ERR_INVALID, "no particles uploaded");
+    if (e->world > 1) return fail_sharded(e, "p3d_step");
     CU(cudaSetDevice(e->device));
     return run_steps(e, prm, P, ts, n_steps);
 }
@@ -992,6 +1009,7 @@ int p3d_update(p3d_engine *e, const p3d_params *prm, float ts, const p3d_particl
     if ((rc = canonicalise(prm, P))) return rc;  // src/lib.rs:132 comes first in the reference too
     if (n == 0) return P3D_OK;                   // src/lib.rs:135-171 with an empty Vec is a no-op
     if (!in || !out) return fail(P3D_ERR_INVALID, "in/out is null");
+    if (e->world > 1) return fail_sharded(e, "p3d_update");
     CU(cudaSetDevice(e->device));
     if ((rc = p3d_upload(e, in, n, prm->id_count))) return rc;
     if ((rc = run_steps(e, prm, P, ts, 1))) return rc;

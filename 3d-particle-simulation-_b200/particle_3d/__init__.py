@@ -60,8 +60,10 @@ class Engine:
     def make_params(world_size, coefficient, interaction_force, min_pull_ratio, particle_effect_radius,
                     id_count, attraction_matrix, walls=False, acceleration=(0.0, 0.0, 0.0)):
         A = np.ascontiguousarray(np.asarray(attraction_matrix, dtype=np.float32).ravel())
-        if A.size != int(id_count) * int(id_count):
-            raise IndexError("attraction_matrix must hold id_count*id_count entries (src/lib.rs:225-228)")
+        # the reference indexes `attraction_matrix[id * id_count + other_id]` (src/lib.rs:225-228): a longer Vec is
+        # fine (only the first id_count^2 entries can be reached by valid ids), a shorter one panics
+        if A.size < int(id_count) * int(id_count):
+            raise IndexError("attraction_matrix is shorter than id_count*id_count entries (src/lib.rs:225-228)")
         p = _abi.Params()
         p.world_size = world_size
         p.coefficient = coefficient

@@ -136,7 +136,8 @@ enum p3d_buffer {
 int p3d_device_buffer(p3d_engine *eng, int which, void **dev_ptr, size_t *n_slots);
 /* Shard = the slot range this rank integrates and, for the force pass, its share of block rows.
  * world==1 restores single-GPU behaviour.  Call BEFORE p3d_upload: the slot layout is padded so that
- * all ranks own equally many slots. */
+ * all ranks own equally many slots.  While world > 1 the whole-step calls (p3d_update, p3d_step) return
+ * P3D_ERR_INVALID: a step then needs the driver's collectives between the p3d_shard_* calls below. */
 int p3d_set_shard(p3d_engine *eng, int rank, int world);
 int p3d_shard_range(p3d_engine *eng, size_t *slot_begin, size_t *slot_end);
 /* One step split at the collectives a multi-GPU driver inserts:

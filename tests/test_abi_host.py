@@ -157,3 +157,14 @@ def test_pair_kernel_inner_loop_is_the_measured_schedule():
     got = [x.replace(".F32x2.HI_LO", "").strip() for x in best]
     if got != want:
         warnings.warn("k_force_pair's inner loop is scheduled differently from the measured build: re-measure it")
+
+
+def test_make_params_matrix_length(default_params):
+    """src/lib.rs:225-228 indexes `attraction_matrix[id * id_count + other]`: longer than id_count^2 is legal
+    (stride id_count, the tail is never reached), shorter is the reference's index panic."""
+    import particle_3d as p3
+
+    P = p3.Engine.make_params(**dict(default_params, id_count=3))  # 25 entries, 9 needed
+    assert P.id_count == 3 and [P.attraction_matrix[k] for k in range(9)] == default_params["attraction_matrix"][:9]
+    with pytest.raises(IndexError):
+        p3.Engine.make_params(**dict(default_params, id_count=6))  # 25 entries, 36 needed
