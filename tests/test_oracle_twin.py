@@ -102,3 +102,15 @@ def test_twin_errors(default_params):
     close["id"][0] = 9
     with pytest.raises(IndexError):
         twin.update(default_params, TS, close)
+
+
+def test_twin_reproduces_the_committed_default_scene_fixture(default_params):
+    """BASELINE config 1 (default scene, N = 1000): the fixture the GPU tests are held against is the C oracle's
+    output; the twin must land on the same bits — state and total forces, the 28 double-visited particles included."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "default_scene_n1000_seed42.npz"))
+    assert int(g["affected1"].sum()) > 0
+    out, force = twin.update(default_params, TS, g["start"])
+    assert np.array_equal(force, g["faithful_force1"])
+    _same(out, g["faithful_step1"])
