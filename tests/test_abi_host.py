@@ -10,6 +10,7 @@ import particle_3d as p3
 from particle_3d import _abi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "3d-particle-simulation-_b200")
 
 
 def _declared_functions():
@@ -168,3 +169,26 @@ def test_make_params_matrix_length(default_params):
     assert P.id_count == 3 and [P.attraction_matrix[k] for k in range(9)] == default_params["attraction_matrix"][:9]
     with pytest.raises(IndexError):
         p3.Engine.make_params(**dict(default_params, id_count=6))  # 25 entries, 36 needed
+
+
+def test_compiled_consumers_build_and_fail_loudly_without_a_device(tmp_path):
+    """The C++ mirror (host/particle_3d.hpp + headless.cpp) and the C99 consumer (tests/c/abi_smoke.c) compile and
+    link against libp3d.so on a box without a GPU, and there they stop with the engine's error — the C++ mirror
+    with Rust's panic exit code 101 — instead of computing anything on the CPU."""
+    import subprocess
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a CUDA device")
+    r = subprocess.run(["make", "-C", PKG, "headless"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([os.path.join(PKG, "headless"), "1000", "2"], capture_output=True, text=True)
+    assert r.returncode == 101 and "no CPU fallback" in r.stderr and r.stdout == ""
+    exe = tmp_path / "abi_smoke"
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-L", PKG, "-lp3d", f"-Wl,-rpath,{PKG}", "-lm",
+                        "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
