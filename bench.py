@@ -145,6 +145,33 @@ def weak_particles(gpus: int) -> int:
     return int(round(N_DEFAULT * (g ** 0.5) / unit)) * unit
 
 
+def multi_gpu_roofline(n: int, world: int, ms_per_step: float, sm_count: int, sm_max_mhz: float, phases=None) -> dict:
+    """FP32 roofline of a sharded run (BASELINE.json configs[3] and [4] ask for the fraction at every GPU count).
+    The job evaluates N^2 ordered pairs per step on `world` GPUs, so the denominator is world x the per-GPU FP32 FMA
+    peak.  `achieved` divides by the WHOLE timed step (slowest rank; force pass + exchange + integrate), which is
+    what the job delivers; the force pass alone, from the per-rank CUDA-event diagnostic, is reported beside it."""
+    peak_gpu = sm_count * 128 * 2 * float(sm_max_mhz) * 1e6 / 1e12
+    flops = float(n) * n * FLOP_PER_INTERACTION
+    achieved = flops / (ms_per_step * 1e-3) / 1e12
+    out = {
+        "kernel": "whole sharded step on the slowest rank: force pass (k_force_pair + k_force_bxb + partition) + "
+                  "exchange/integrate",
+        "bound": "fp32_fma", "achieved": achieved, "peak": peak_gpu * world, "unit": "TFLOP/s",
+        "frac": achieved / (peak_gpu * world),
+        "peak_source": f"{world} GPUs x {sm_count} SMs x 128 lanes x 2 flop x {float(sm_max_mhz):.0f} MHz",
+        "algorithmic_flops_per_step": flops, "flop_per_interaction": FLOP_PER_INTERACTION,
+        "per_gpu": {"achieved": achieved / world, "peak": peak_gpu},
+        "traffic": None,
+    }
+    force = [float(x) for x in (phases or {}).get("force", []) if x and x > 0]
+    if force:
+        slowest = max(force)
+        out["force_pass"] = {"ms_slowest_rank": slowest, "achieved": flops / (slowest * 1e-3) / 1e12,
+                             "frac": flops / (slowest * 1e-3) / 1e12 / (peak_gpu * world),
+                             "what": "each rank's share of the block rows, CUDA events on its own stream (diagnostic steps)"}
+    return out
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -495,6 +522,15 @@ def run_engine(args):
                     "(first barrier) | fused P2P integrate + second barrier",
             "force": [round(a[0], 3) for a in allp], "wait_for_slowest": [round(a[1], 3) for a in allp],
             "exchange_integrate": [round(a[2], 3) for a in allp]}
+
+    if world > 1 and rank == 0:
+        try:  # (no collective in here: only rank 0 runs it)
+            prop = torch.cuda.get_device_properties(local)
+            sm_max_mhz = (measured_peaks() or {}).get("sm_max_mhz") or clock_summary.get("sm_max_mhz") or 1965.0
+            line["roofline"] = multi_gpu_roofline(n, world, ms_per_step, prop.multi_processor_count, sm_max_mhz,
+                                                  line.get("phases_ms_per_rank"))
+        except Exception as ex:  # a reporting extra must never take the bench line down
+            line["roofline"] = {"error": repr(ex)}
 
     # ---------------- the other cloud (north_star: uniform AND clustered clouds at every GPU count) ----------------
     if not args.no_other_cloud and n >= 4096:

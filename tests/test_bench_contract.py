@@ -69,3 +69,20 @@ def test_weak_scaling_particle_counts():
         assert n % (256 * g) == 0
         assert abs(n * n / g / 1048576.0 ** 2 - 1.0) < 2e-3
     assert bench.weak_particles(8) == 2965504  # the run recorded in DESIGN.md
+
+
+def test_multi_gpu_roofline_arithmetic():
+    """The sharded run's roofline object: N^2 x 20 flop over the whole step against world x the per-GPU FP32 peak,
+    with the measured round-1 numbers (8 GPUs, N = 1M, 41.55 ms/step, force pass 41.31 ms on the slowest rank)."""
+    import bench
+
+    r = bench.multi_gpu_roofline(1048576, 8, 41.55, 148, 1965.0,
+                                 {"force": [41.19, 41.31, 41.2, 41.25, 41.3, 41.22, 41.28, 41.21]})
+    assert r["bound"] == "fp32_fma" and r["unit"] == "TFLOP/s"
+    assert abs(r["peak"] - 8 * 74.44992) < 1e-6
+    assert abs(r["achieved"] - 1048576.0 ** 2 * 20 / 41.55e-3 / 1e12) < 1e-6
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and 0.88 < r["frac"] < 0.90
+    assert abs(r["per_gpu"]["achieved"] * 8 - r["achieved"]) < 1e-9
+    assert r["force_pass"]["ms_slowest_rank"] == 41.31 and r["force_pass"]["frac"] > r["frac"]
+    # no per-rank diagnostic (--no-fused): the whole-step figures alone
+    assert "force_pass" not in bench.multi_gpu_roofline(1048576, 2, 164.3, 148, 1965.0, None)
