@@ -28,3 +28,27 @@ def test_oracle_is_clean_under_asan_and_ubsan(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "clean" in r.stdout, r.stdout + r.stderr
     assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr
+
+
+def test_host_only_product_code_is_clean_under_asan_and_ubsan(tmp_path):
+    """csrc/p3d_scene.cpp (seeded generators, default scene) is the one part of the product that runs on the host
+    alone; it gets the same treatment (the rest of libp3d.so needs the CUDA runtime and a device)."""
+    san = ["-g", "-O1", "-fsanitize=address,undefined,float-cast-overflow", "-fno-sanitize-recover=all"]
+    inc = ["-I", os.path.join(ROOT, "include")]
+    steps = [
+        ["/usr/bin/g++", "-std=c++17", *san, *inc, "-c", "-o", str(tmp_path / "scene.o"),
+         os.path.join(ROOT, "3d-particle-simulation-_b200", "csrc", "p3d_scene.cpp")],
+        ["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", *san, *inc, "-c", "-o", str(tmp_path / "drv.o"),
+         os.path.join(ROOT, "tests", "c", "scene_sanitize.c")],
+        ["/usr/bin/g++", "-fsanitize=address,undefined", "-o", str(tmp_path / "scene_sanitize"), str(tmp_path / "drv.o"),
+         str(tmp_path / "scene.o"), "-lm"],
+    ]
+    for cmd in steps:
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0 and ("libasan" in r.stderr or "libubsan" in r.stderr or "-lasan" in r.stderr):
+            pytest.skip("this toolchain ships no sanitizer runtimes")
+        assert r.returncode == 0, r.stderr
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1")
+    env.pop("LD_PRELOAD", None)
+    r = subprocess.run([str(tmp_path / "scene_sanitize")], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and "clean" in r.stdout, r.stdout + r.stderr
