@@ -13,6 +13,8 @@
  * evaluation over the 27 periodic images which must agree with the cell-list walk,
  * (iv) a second restatement written separately in Python (oracle/lib_rs_twin.py) that must
  * agree with this file's faithful mode bit for bit (tests/test_oracle_twin.py).
+ * (v) hash_cell against CPython's own SipHash-1-3 with a zero key (PYTHONHASHSEED=0), an implementation
+ * written by neither of us (tests/test_oracle_kat.py).
  */
 #ifndef P3D_ORACLE_H
 #define P3D_ORACLE_H

@@ -160,3 +160,33 @@ def test_coincident_particles_do_not_interact(default_params):
     p["px"] = 1.25
     r = O.update(default_params, TS, p, want_force=True)
     assert not r["force"].any()
+
+
+def test_hash_cell_against_cpythons_own_siphash13():
+    """An implementation we did not write: CPython >= 3.11 hashes `bytes` with SipHash-1-3, and PYTHONHASHSEED=0
+    zeroes its key — the very function Rust's `DefaultHasher::new()` computes (src/lib.rs:46-52 feeds it the three
+    cell coordinates as 8 little-endian bytes each).  2,000 random cells, saturated and negative ones included."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    rng = np.random.default_rng(12)
+    cells = [tuple(int(v) for v in rng.integers(-(2 ** 63), 2 ** 63 - 1, 3, dtype=np.int64)) for _ in range(1000)]
+    cells += [tuple(int(v) for v in rng.integers(-60, 60, 3)) for _ in range(1000)]
+    cells += [(2 ** 63 - 1, -(2 ** 63), 0), (0, 0, 0), (-1, -1, -1)]
+    code = ("import sys, json\n"
+            "assert sys.hash_info.algorithm == 'siphash13' and sys.hash_info.hash_bits == 64, sys.hash_info\n"
+            "cells = json.load(sys.stdin)\n"
+            "print(json.dumps([hash(b''.join(int(c).to_bytes(8, 'little', signed=True) for c in cell)) & (2**64 - 1)"
+            " for cell in cells]))\n")
+    env = dict(os.environ, PYTHONHASHSEED="0")
+    r = subprocess.run([sys.executable, "-c", code], input=json.dumps(cells), capture_output=True, text=True, env=env)
+    if r.returncode != 0 and "hash_info" in r.stderr:
+        pytest.skip("this interpreter does not hash bytes with 64-bit SipHash-1-3")
+    assert r.returncode == 0, r.stderr
+    theirs = json.loads(r.stdout)
+    ours = [O.hash_cell(*cell) for cell in cells]
+    # CPython maps a hash of -1 to -2 (an error sentinel): such a value cannot be told apart, skip it if it ever occurs
+    assert all(a == b for a, b in zip(ours, theirs) if b != 2 ** 64 - 2)
+    assert sum(b != 2 ** 64 - 2 for b in theirs) >= len(cells) - 1
