@@ -114,3 +114,46 @@ def test_twin_reproduces_the_committed_default_scene_fixture(default_params):
     out, force = twin.update(default_params, TS, g["start"])
     assert np.array_equal(force, g["faithful_force1"])
     _same(out, g["faithful_step1"])
+
+
+def _numpy_all_pairs_forces(prm, parts):
+    """All N x N x 27 (particle, neighbour, image) triples, vectorised, no cells and no hash: what the reference's
+    neighbour search is meant to find.  Image positions and the cutoff test use the reference's float32 arithmetic
+    (src/lib.rs:190-192,211-220); the force sum itself is accumulated in float64."""
+    W, r, m = np.float32(prm["world_size"]), np.float32(prm["particle_effect_radius"]), np.float32(prm["min_pull_ratio"])
+    T = int(prm["id_count"])
+    A = np.asarray(prm["attraction_matrix"], np.float32).reshape(-1)[: T * T].reshape(T, T)
+    pos = np.stack([parts["px"], parts["py"], parts["pz"]], 1).astype(np.float32)
+    a = A[parts["id"][:, None], parts["id"][None, :]].astype(np.float32)
+    total = np.zeros((len(parts), 3))
+    with np.errstate(all="ignore"):
+        for ox in (-1, 0, 1):
+            for oy in (-1, 0, 1):
+                for oz in (-1, 0, 1):
+                    shifted = pos + np.array([ox, oy, oz], np.float32) * W            # float32, like the reference
+                    rel = pos[None, :, :] - shifted[:, None, :]                       # [i, j] = other - (self + offset)
+                    d2 = (rel[..., 0] * rel[..., 0] + rel[..., 1] * rel[..., 1]) + rel[..., 2] * rel[..., 2]
+                    hit = (d2 > 0) & (d2 < r * r)
+                    d = np.sqrt(d2)
+                    f = np.where(d < m, d / m - np.float32(1),
+                                 np.where((m < d) & (d < 1), a * (np.float32(1) - np.abs(np.float32(2) * d - np.float32(1) - m)
+                                                                   / (np.float32(1) - m)), np.float32(0)))
+                    contrib = np.where(hit[..., None], rel / d[..., None] * f[..., None], 0).astype(np.float64)
+                    total += contrib.sum(1)
+    return total
+
+
+@pytest.mark.parametrize("name,n,W,over", [("default", 600, 8.4, {}), ("two_radii", 300, 4.0, {}),
+                                            ("short_cutoff", 500, 6.0, {"particle_effect_radius": 0.7}),
+                                            ("m_above_one", 400, 7.0, {"min_pull_ratio": 1.5, "particle_effect_radius": 2.5})],
+                         ids=lambda v: v if isinstance(v, str) else None)
+def test_ideal_mode_equals_a_vectorised_all_pairs_sum(default_params, name, n, W, over):
+    """The oracle's IDEAL mode (the physics the GPU engine implements by default) against a numpy evaluation of every
+    (particle, neighbour, image) triple written here: the spatial hash must find each in-range triple exactly once."""
+    prm = dict(default_params, world_size=W, **over)
+    parts = _cloud(W, n, seed=31 + n)
+    want = _numpy_all_pairs_forces(prm, parts)
+    got = O.update(prm, TS, parts, mode=O.IDEAL, want_force=True, nthreads=1)["force"].astype(np.float64)
+    frms = np.sqrt((want ** 2).sum(1).mean())
+    err = np.linalg.norm(got - want, axis=1) / np.maximum(np.linalg.norm(want, axis=1), frms)
+    assert frms > 0 and err.max() < 5e-6, err.max()   # float32 summation of ~30 terms against float64
