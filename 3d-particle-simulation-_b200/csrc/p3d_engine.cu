@@ -48,6 +48,7 @@ constexpr int kMaxTimedSteps = 512;
 constexpr int kEv = 5;  // events per timed step
 constexpr int kRefTile = 128;       // threads per CTA of the reference-order kernel
 constexpr int kOutOfBoxCellsMin = 32768;  // all-pairs path, out-of-box input, single-step call: cell list from this n
+constexpr int kPinWords = 128;     // pinned scratch words per engine (>= P3D_MAX_TYPES + 2)
 constexpr int kCellsAutoMin = 192;  // P3D_FORCE_AUTO uses the cell list from this n (its ~12 launches cost ~35 us),
                                     // the single-launch reference-order kernel below
 
@@ -55,13 +56,15 @@ template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;
+    // Grow-only (contents are not preserved).  The new block is allocated BEFORE the old one is freed, so a
+    // failed grow leaves the buffer as it was (and the engine's n / n_slots still describe valid memory).
     int ensure(size_t n) {
         if (n <= cap) return P3D_OK;
+        const size_t want = n + n / 8 + 64;  // slack: the host may add particles (main.rs:274-279)
+        T *fresh = nullptr;
+        CU(cudaMalloc(&fresh, want * sizeof(T)));
         if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        const size_t want = n + n / 8 + 64;  // grow-only with slack (host may add particles, main.rs:274-279)
-        CU(cudaMalloc(&p, want * sizeof(T)));
+        p = fresh;
         cap = want;
         return P3D_OK;
     }
@@ -108,6 +111,11 @@ struct p3d_engine {
     DevBuf<double> diag;
     int cur = 0;            // which pos buffer is current
     int parity = 0;         // which flag word describes the current positions
+    bool upload_timed = false;  // ev_call[0..1] were recorded by the upload in flight
+    size_t n_staged = 0;    // particles in the AoS staging array `aos` awaiting p3d_upload_commit (sharded upload)
+    uint32_t T_staged = 0;
+    uint32_t *host_pin = nullptr;  // pinned scratch (kPinWords words): per-type totals and flags come back without
+                                   // the implicit synchronisation of a copy into pageable memory
 
     std::vector<uint8_t> seg_type_h;
 
@@ -127,8 +135,14 @@ struct p3d_engine {
 
     // sharding
     int rank = 0, world = 1;
-    // peer memory (CUDA IPC): [rank][0]=frc, [1]=pos[0], [2]=pos[1]; own entries are the local pointers
-    void *peer_ptr[8][3] = {};
+    // A handle made by p3d_create_multi drives one member engine per device (rank g of members.size()) from the
+    // calling thread; the members' peer tables point straight at each other's buffers (one process, peer access).
+    std::vector<p3d_engine *> members;
+    std::vector<cudaEvent_t> ev_bar;   // one per member: recorded at each cross-device barrier
+    bool is_member = false;
+    // peer memory (CUDA IPC or, inside a multi-device handle, plain peer access):
+    // [rank][0]=frc, [1]=pos[0], [2]=pos[1], [3]=vel; own entries are the local pointers
+    void *peer_ptr[8][4] = {};
     bool peer_open[8] = {};
     bool peers_ready = false;
     bool ipc_exported = false;  // frc/pos were handed to peers: they must not be reallocated until p3d_ipc_close
@@ -182,14 +196,15 @@ int canonicalise(const p3d_params *prm, DevParams &P) {
 
 int ensure_common(p3d_engine *e, size_t n, size_t ns) {
     int rc;
-    if (e->ipc_exported && ((size_t)ns > e->pos[0].cap || (size_t)ns > e->pos[1].cap || (size_t)ns > e->frc.cap))
-        return fail(P3D_ERR_INVALID, "upload needs %zu slots but the position/force buffers are exported to peer GPUs "
+    if (e->ipc_exported && ((size_t)ns > e->pos[0].cap || (size_t)ns > e->pos[1].cap || (size_t)ns > e->frc.cap ||
+                            (size_t)ns > e->vel.cap))
+        return fail(P3D_ERR_INVALID, "upload needs %zu slots but the position/velocity/force buffers are exported to peer GPUs "
                     "(p3d_ipc_export); call p3d_ipc_close on every rank, upload, then export/import again", (size_t)ns);
     if ((rc = e->pos[0].ensure(ns))) return rc;
     if ((rc = e->pos[1].ensure(ns))) return rc;
     if ((rc = e->vel.ensure(ns))) return rc;
     if ((rc = e->frc.ensure(ns))) return rc;
-    if ((rc = e->aos.ensure((n ? n : 1) * 7))) return rc;
+    (void)n;  // (the AoS staging array was sized by stage_input)
     if ((rc = e->matrix.ensure(P3D_MAX_TYPES * P3D_MAX_TYPES))) return rc;
     if ((rc = e->flags.ensure(4))) return rc;
     if ((rc = e->diag.ensure(8))) return rc;
@@ -207,86 +222,97 @@ int fail_sharded(const p3d_engine *e, const char *call) {
                 call, e->rank, e->world);
 }
 
+// ---- upload, phase 1: the caller's particles [i_begin, i_end) of n -> the device-side AoS staging array ----
+// Asynchronous on the engine stream.  The array is sized for world * ceil(n / world) particles so that a
+// one-process-per-GPU driver can all-gather equal parts into it (P3D_BUF_AOS).
+size_t staged_part(size_t n, int world) { return (n + (size_t)world - 1) / (size_t)world; }
+
+int stage_input(p3d_engine *e, const p3d_particle *part, size_t i_begin, size_t i_end, size_t n) {
+    if (n > (size_t)0x7fff0000) return fail(P3D_ERR_INVALID, "n too large");
+    int rc;
+    const size_t cap = std::max<size_t>(staged_part(n, e->world) * (size_t)e->world, 1);
+    if ((rc = e->aos.ensure(cap * 7))) return rc;
+    if (i_end > i_begin)
+        CU(cudaMemcpyAsync(e->aos.p + i_begin * 7, part, (i_end - i_begin) * sizeof(p3d_particle),
+                           cudaMemcpyHostToDevice, e->stream));
+    return P3D_OK;
+}
+
 // Identity layout (slot = caller index): all the cell-list and reference-order kernels need.  No host
 // pass over the particles; ids are validated on the device by k_pack.
 int build_layout_identity(p3d_engine *e, size_t n, uint32_t T) {
-    if (n > (size_t)0x7fff0000) return fail(P3D_ERR_INVALID, "n too large");
     e->B = 128;
     const size_t unit = (size_t)e->B * (size_t)e->world;
     const size_t ns = (std::max<size_t>(n, 1) + unit - 1) / unit * unit;
+    int rc;
+    if ((rc = ensure_common(e, n, ns))) return rc;
     e->n_slots = (int)ns;
     e->M = e->n_slots / e->B;
     e->n = n;
     e->T = T;
     e->typed = false;
     e->layout_version++;
-    int rc;
-    if ((rc = ensure_common(e, n, ns))) return rc;
     CU(cudaMemsetAsync(e->flags.p, 0, 4 * sizeof(int), e->stream));
     return P3D_OK;
 }
 
 // Type-grouped layout for the pair kernel.  The counting sort by type id runs on the device (k_type_hist,
 // k_type_scan, later k_pack_typed); the host only sees the T per-type totals, from which it derives the
-// block-padded segments.  Copies `in` to the device (the counts need it) and returns with the stream idle.
-int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T, bool timed) {
-    if (n > (size_t)0x7fff0000) return fail(P3D_ERR_INVALID, "n too large");
+// block-padded segments.
+// Part 1 (asynchronous): per-type counts of the staged AoS array and the smallest caller index with a bad id,
+// copied into the engine's pinned scratch ([0..T) counts, [T] bad index).  The caller synchronises the stream.
+int layout_count_async(p3d_engine *e, size_t n, uint32_t T) {
     static_assert(P3D_MAX_TYPES == kTypeMax, "k_type_* kernels are sized for P3D_MAX_TYPES");
+    static_assert(P3D_MAX_TYPES + 2 <= kPinWords, "pinned scratch holds the type totals");
     cudaStream_t st = e->stream;
     int rc;
     const size_t n_ctas = (n + kTypeThreads - 1) / kTypeThreads;
-    if ((rc = e->aos.ensure((n ? n : 1) * 7))) return rc;
     if ((rc = e->type_cnt.ensure(2 * std::max<size_t>(n_ctas, 1) * T + P3D_MAX_TYPES))) return rc;
     if ((rc = e->flags.ensure(4))) return rc;
+    for (uint32_t t = 0; t <= T; ++t) e->host_pin[t] = 0u;
+    e->host_pin[T] = 0x7f7f7f7fu;
+    if (!n) return P3D_OK;
     uint32_t *cta_cnt = e->type_cnt.p, *cta_off = cta_cnt + n_ctas * T, *total = cta_off + n_ctas * T;
-    std::vector<uint32_t> count(T, 0);
-    if (n) {
-        CU(cudaMemcpyAsync(e->aos.p, in, n * sizeof(p3d_particle), cudaMemcpyHostToDevice, st));
-        if (timed) CU(cudaEventRecord(e->ev_call[1], st));
-        CU(cudaMemsetAsync(e->flags.p + 2, 0x7f, sizeof(int), st));  // 0x7f7f7f7f: larger than any index
-        k_type_hist<<<(unsigned)n_ctas, kTypeThreads, 0, st>>>(e->aos.p, (int)n, T, cta_cnt, e->flags.p + 2);
-        k_type_scan<<<T, 1024, 0, st>>>(cta_cnt, cta_off, (int)n_ctas, T, total);
-        e->counters[0] += 2;
-        CU(cudaGetLastError());
-        int bad = 0;
-        CU(cudaMemcpyAsync(count.data(), total, T * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(&bad, e->flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if ((size_t)bad < n)
-            return fail(P3D_ERR_BAD_ID, "particle %d has id %u >= id_count %u (src/lib.rs:225-228)", bad, in[bad].id, T);
-    } else if (timed) {
-        CU(cudaEventRecord(e->ev_call[1], st));
+    CU(cudaMemsetAsync(e->flags.p + 2, 0x7f, sizeof(int), st));  // 0x7f7f7f7f: larger than any index
+    k_type_hist<<<(unsigned)n_ctas, kTypeThreads, 0, st>>>(e->aos.p, (int)n, T, cta_cnt, e->flags.p + 2);
+    k_type_scan<<<T, 1024, 0, st>>>(cta_cnt, cta_off, (int)n_ctas, T, total);
+    e->counters[0] += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(e->host_pin, total, T * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(e->host_pin + T, e->flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+    return P3D_OK;
+}
+
+// Part 2 (the stream has been synchronised): segments from the totals, buffers, small tables.
+int layout_finish(p3d_engine *e, size_t n, uint32_t T) {
+    cudaStream_t st = e->stream;
+    int rc;
+    const uint32_t *count = e->host_pin;
+    if ((size_t)e->host_pin[T] < n) {
+        const size_t bad = e->host_pin[T];
+        uint32_t id = 0;
+        CU(cudaMemcpy(&id, e->aos.p + bad * 7 + 6, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        return fail(P3D_ERR_BAD_ID, "particle %zu has id %u >= id_count %u (src/lib.rs:225-228)", bad, id, T);
     }
-    e->typed = true;
-    e->layout_version++;
-    e->B = e->B_next ? e->B_next : (n >= 65536 ? 256 : 128);
-    const int B = e->B;
-    e->seg_start_h.assign(T, 0);
-    e->seg_end_h.assign(T, 0);
+    const int B = e->B_next ? e->B_next : (n >= 65536 ? 256 : 128);
+    std::vector<int> seg_start(T, 0), seg_end(T, 0);
     size_t at = 0;
     for (uint32_t t = 0; t < T; ++t) {
-        e->seg_start_h[t] = (int)at;
+        seg_start[t] = (int)at;
         at += ((size_t)count[t] + B - 1) / B * B;
-        e->seg_end_h[t] = (int)at;
+        seg_end[t] = (int)at;
     }
     if (at == 0) at = B;  // keep one (ghost) block so kernels always have a valid grid
     {   // equal shards for the multi-GPU all-gather: the last type's region absorbs the padding blocks
         const size_t unit = (size_t)B * (size_t)e->world;
         at = (at + unit - 1) / unit * unit;
-        e->seg_end_h[T - 1] = (int)at;
+        seg_end[T - 1] = (int)at;
     }
-    e->n_slots = (int)at;
-    e->M = e->n_slots / B;
-    e->n = n;
-    e->T = T;
-    e->seg_type_h.assign(e->M, 0);
-    for (uint32_t t = 0; t < T; ++t)
-        for (int b = e->seg_start_h[t] / B; b < e->seg_end_h[t] / B; ++b) e->seg_type_h[b] = (uint8_t)t;
-
-    const size_t ns = (size_t)e->n_slots;
-    if (e->ipc_exported && ((size_t)ns > e->pos[0].cap || (size_t)ns > e->pos[1].cap || (size_t)ns > e->frc.cap))
-        return fail(P3D_ERR_INVALID, "upload needs %zu slots but the position/force buffers are exported to peer GPUs "
-                    "(p3d_ipc_export); call p3d_ipc_close on every rank, upload, then export/import again", (size_t)ns);
+    const size_t ns = at;
+    const size_t M = ns / B;
+    if (e->ipc_exported && (ns > e->pos[0].cap || ns > e->pos[1].cap || ns > e->frc.cap || ns > e->vel.cap))
+        return fail(P3D_ERR_INVALID, "upload needs %zu slots but the position/velocity/force buffers are exported to peer GPUs "
+                    "(p3d_ipc_export); call p3d_ipc_close on every rank, upload, then export/import again", ns);
     if ((rc = e->pos[0].ensure(ns))) return rc;
     if ((rc = e->pos[1].ensure(ns))) return rc;
     if ((rc = e->vel.ensure(ns))) return rc;
@@ -297,8 +323,8 @@ int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T, bo
     if ((rc = e->sy.ensure(ns))) return rc;
     if ((rc = e->sz.ensure(ns))) return rc;
     if ((rc = e->slot_of.ensure(n ? n : 1))) return rc;
-    if ((rc = e->seg_type.ensure((size_t)e->M))) return rc;
-    if ((rc = e->bclass.ensure((size_t)e->M))) return rc;
+    if ((rc = e->seg_type.ensure(M))) return rc;
+    if ((rc = e->bclass.ensure(M))) return rc;
     if ((rc = e->seg_start.ensure(P3D_MAX_TYPES))) return rc;
     if ((rc = e->seg_end.ensure(P3D_MAX_TYPES))) return rc;
     if ((rc = e->cnt.ensure(2 * P3D_MAX_TYPES))) return rc;
@@ -306,6 +332,19 @@ int build_layout(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t T, bo
     if ((rc = e->cta_off.ensure(ns / kPartThreads + 1))) return rc;
     if ((rc = e->matrix.ensure(P3D_MAX_TYPES * P3D_MAX_TYPES))) return rc;
     if ((rc = e->diag.ensure(8))) return rc;
+    // every allocation succeeded: only now does the engine's layout change
+    e->typed = true;
+    e->layout_version++;
+    e->B = B;
+    e->seg_start_h = seg_start;
+    e->seg_end_h = seg_end;
+    e->n_slots = (int)ns;
+    e->M = (int)M;
+    e->n = n;
+    e->T = T;
+    e->seg_type_h.assign(e->M, 0);
+    for (uint32_t t = 0; t < T; ++t)
+        for (int b = e->seg_start_h[t] / B; b < e->seg_end_h[t] / B; ++b) e->seg_type_h[b] = (uint8_t)t;
 
     // small host arrays owned by the engine (they stay valid until the next upload, which first drains the stream)
     CU(cudaMemcpyAsync(e->seg_type.p, e->seg_type_h.data(), (size_t)e->M, cudaMemcpyHostToDevice, st));
@@ -335,15 +374,6 @@ int launch_pack(p3d_engine *e, size_t n) {
                                                             e->flags.p + 2);
         e->counters[0]++;
     }
-    CU(cudaGetLastError());
-    return P3D_OK;
-}
-
-int launch_unpack(p3d_engine *e, size_t n) {
-    if (!n) return P3D_OK;
-    k_unpack<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->pos[e->cur].p, e->vel.p,
-                                                                 e->typed ? e->slot_of.p : nullptr, e->aos.p, (int)n);
-    e->counters[0]++;
     CU(cudaGetLastError());
     return P3D_OK;
 }
@@ -753,6 +783,16 @@ int run_steps(p3d_engine *e, const p3d_params *prm, const DevParams &P, float ts
 }  // namespace
 
 // =============================================================================================
+// multi-device handle (p3d_create_multi): defined at the end of this file
+static int multi_upload(p3d_engine *grp, const p3d_particle *in, size_t n, uint32_t id_count);
+static int multi_step(p3d_engine *grp, const p3d_params *prm, float ts, int n_steps);
+static int multi_download(p3d_engine *grp, p3d_particle *out, size_t n);
+static int multi_download_forces(p3d_engine *grp, float *out_xyz, size_t n);
+static int multi_not_supported(const char *call) {
+    return fail(P3D_ERR_INVALID, "%s is not available on a multi-device handle (p3d_create_multi): it drives its devices "
+                "itself - use p3d_upload / p3d_step / p3d_update / p3d_download", call);
+}
+
 extern "C" {
 
 int p3d_abi_version(void) { return P3D_ABI_VERSION; }
@@ -796,6 +836,8 @@ int p3d_create(int device, p3d_engine **out) {
     if (ce == cudaSuccess) ce = cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, prio_hi);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+    uint32_t *pin = nullptr;
+    if (ce == cudaSuccess) ce = cudaMallocHost(&pin, kPinWords * sizeof(uint32_t));
     if (ce != cudaSuccess) {  // nothing half-made is left behind
         if (ev_join) cudaEventDestroy(ev_join);
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -804,6 +846,7 @@ int p3d_create(int device, p3d_engine **out) {
         return fail(P3D_ERR_CUDA, "creating the engine's streams/events failed: %s", cudaGetErrorString(ce));
     }
     p3d_engine *e = new p3d_engine();
+    e->host_pin = pin;
     e->aux_stream = aux;
     e->ev_fork = ev_fork;
     e->ev_join = ev_join;
@@ -817,6 +860,19 @@ int p3d_create(int device, p3d_engine **out) {
 
 void p3d_destroy(p3d_engine *e) {
     if (!e) return;
+    if (!e->members.empty()) {
+        for (p3d_engine *m : e->members) {
+            cudaSetDevice(m->device);
+            cudaStreamSynchronize(m->stream);
+        }
+        for (size_t g = 0; g < e->ev_bar.size(); ++g) {
+            cudaSetDevice(e->members[g % e->members.size()]->device);
+            cudaEventDestroy(e->ev_bar[g]);
+        }
+        for (p3d_engine *m : e->members) p3d_destroy(m);
+        delete e;
+        return;
+    }
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     p3d_ipc_close(e);
@@ -836,17 +892,24 @@ void p3d_destroy(p3d_engine *e) {
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->host_pin) cudaFreeHost(e->host_pin);
     delete e;
 }
 
 int p3d_set_stream(p3d_engine *e, void *cuda_stream) {
     if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (!e->members.empty()) return multi_not_supported("p3d_set_stream");
     e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
     return P3D_OK;
 }
 
 int p3d_set_option(p3d_engine *e, int option, int value) {
     if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (option == P3D_OPT_TIMING && value && !e->members.empty()) return multi_not_supported("per-kernel timing (P3D_OPT_TIMING)");
+    for (p3d_engine *m : e->members) {  // a multi-device handle keeps its members' options identical
+        const int rc = p3d_set_option(m, option, value);
+        if (rc) return rc;
+    }
     switch (option) {
         case P3D_OPT_FORCE_KERNEL:
             if (value < P3D_FORCE_AUTO || value > P3D_FORCE_CELLS) return fail(P3D_ERR_INVALID, "bad force kernel %d", value);
@@ -877,38 +940,31 @@ int p3d_get_option(p3d_engine *e, int option, int *value) {
     }
 }
 
-int p3d_upload(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t id_count) {
-    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
-    if (n && !in) return fail(P3D_ERR_INVALID, "in is null");
-    if (id_count == 0 || id_count > P3D_MAX_TYPES)
-        return fail(P3D_ERR_INVALID, "id_count %u outside 1..%d", id_count, P3D_MAX_TYPES);
-    CU(cudaSetDevice(e->device));
+// Upload, phase 2: layout + pack from the staged AoS array.  `async_counts_done`: the pair layout's count kernels
+// were already queued (multi-device handle: all members count concurrently).  Returns with the stream idle.
+static int upload_commit(p3d_engine *e, size_t n, uint32_t id_count, bool counts_queued) {
     int rc;
-    if (e->opt_timing) {
-        if ((rc = ensure_events(e, 1))) return rc;
-        CU(cudaEventRecord(e->ev_call[0], e->stream));
-    }
-    // The pair kernel needs type-grouped slots (a counting sort by type id, done on the device); every other
-    // kernel runs on the identity layout.  Either way there is no host pass over the particles.
-    if (resolve_force_kernel_for(e, n) == P3D_FORCE_PAIR) {
-        if ((rc = build_layout(e, in, n, id_count, e->opt_timing != 0))) return rc;  // copies `in` itself
+    const bool pair = resolve_force_kernel_for(e, n) == P3D_FORCE_PAIR;
+    if (pair) {
+        if (!counts_queued && (rc = layout_count_async(e, n, id_count))) return rc;
+        CU(cudaStreamSynchronize(e->stream));
+        if ((rc = layout_finish(e, n, id_count))) return rc;
     } else {
         if ((rc = build_layout_identity(e, n, id_count))) return rc;
-        if (n) CU(cudaMemcpyAsync(e->aos.p, in, n * sizeof(p3d_particle), cudaMemcpyHostToDevice, e->stream));
-        if (e->opt_timing) CU(cudaEventRecord(e->ev_call[1], e->stream));
     }
     if ((rc = launch_pack(e, n))) return rc;
-    if (e->opt_timing) CU(cudaEventRecord(e->ev_call[2], e->stream));
-    // `in` may be pageable or reused by the caller: the copy must have consumed it before we return.
+    const bool timed = e->upload_timed;
+    e->upload_timed = false;
+    if (timed) CU(cudaEventRecord(e->ev_call[2], e->stream));
     // The same sync brings back the device-side id check of the identity layout.
-    int bad_id = 0;
-    CU(cudaMemcpyAsync(&bad_id, e->flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    e->host_pin[kPinWords - 1] = 0u;
+    CU(cudaMemcpyAsync(e->host_pin + kPinWords - 1, e->flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    if (e->opt_timing) {
+    if (timed) {
         CU(cudaEventElapsedTime(&e->last_ms[5], e->ev_call[0], e->ev_call[1]));
         CU(cudaEventElapsedTime(&e->last_ms[2], e->ev_call[1], e->ev_call[2]));
     }
-    if (bad_id) {
+    if (!pair && e->host_pin[kPinWords - 1]) {
         e->n = 0;
         e->n_slots = 0;
         return fail(P3D_ERR_BAD_ID, "a particle has id >= id_count %u (src/lib.rs:225-228)", id_count);
@@ -916,16 +972,76 @@ int p3d_upload(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t id_coun
     return P3D_OK;
 }
 
+static int upload_args_ok(p3d_engine *e, const void *in, size_t n, uint32_t id_count) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (n && !in) return fail(P3D_ERR_INVALID, "in is null");
+    if (id_count == 0 || id_count > P3D_MAX_TYPES)
+        return fail(P3D_ERR_INVALID, "id_count %u outside 1..%d", id_count, P3D_MAX_TYPES);
+    return P3D_OK;
+}
+
+int p3d_upload(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t id_count) {
+    int rc;
+    if ((rc = upload_args_ok(e, in, n, id_count))) return rc;
+    if (!e->members.empty()) return multi_upload(e, in, n, id_count);
+    CU(cudaSetDevice(e->device));
+    e->upload_timed = e->opt_timing != 0;
+    if (e->upload_timed) {
+        if ((rc = ensure_events(e, 1))) return rc;
+        CU(cudaEventRecord(e->ev_call[0], e->stream));
+    }
+    // The pair kernel needs type-grouped slots (a counting sort by type id, done on the device); every other
+    // kernel runs on the identity layout.  Either way there is no host pass over the particles.
+    if ((rc = stage_input(e, in, 0, n, n))) return rc;
+    if (e->upload_timed) CU(cudaEventRecord(e->ev_call[1], e->stream));
+    e->n_staged = 0;
+    // `in` may be pageable or reused by the caller: upload_commit returns with the stream idle, i.e. after the copy
+    return upload_commit(e, n, id_count, false);
+}
+
+// Sharded upload for one-process-per-GPU drivers: every rank copies only ITS part of the caller's array over its
+// own PCIe link, the driver all-gathers the staging array over NVLink, then every rank builds the layout.
+int p3d_upload_part(p3d_engine *e, const p3d_particle *part, size_t i_begin, size_t i_end, size_t n, uint32_t id_count) {
+    int rc;
+    if ((rc = upload_args_ok(e, part, i_end > i_begin ? 1 : 0, id_count))) return rc;
+    if (!e->members.empty() || e->is_member) return fail(P3D_ERR_INVALID, "p3d_upload_part on a multi-device handle: use p3d_upload");
+    if (i_begin > i_end || i_end > n) return fail(P3D_ERR_INVALID, "bad part [%zu, %zu) of %zu", i_begin, i_end, n);
+    CU(cudaSetDevice(e->device));
+    e->upload_timed = e->opt_timing != 0;
+    if (e->upload_timed) {
+        if ((rc = ensure_events(e, 1))) return rc;
+        CU(cudaEventRecord(e->ev_call[0], e->stream));
+    }
+    if ((rc = stage_input(e, part, i_begin, i_end, n))) return rc;
+    if (e->upload_timed) CU(cudaEventRecord(e->ev_call[1], e->stream));
+    e->n_staged = n;
+    e->T_staged = id_count;
+    CU(cudaStreamSynchronize(e->stream));  // `part` may be pageable or reused by the caller
+    return P3D_OK;
+}
+
+int p3d_upload_commit(p3d_engine *e) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (e->T_staged == 0) return fail(P3D_ERR_INVALID, "nothing staged: call p3d_upload_part first");
+    CU(cudaSetDevice(e->device));
+    const size_t n = e->n_staged;
+    const uint32_t T = e->T_staged;
+    e->n_staged = 0;
+    e->T_staged = 0;
+    return upload_commit(e, n, T, false);
+}
+
 int p3d_step(p3d_engine *e, const p3d_params *prm, float ts, int n_steps) {
     if (!e) return fail(P3D_ERR_INVALID, "engine is null");
     if (n_steps < 0) return fail(P3D_ERR_INVALID, "n_steps < 0");
+    if (!e->members.empty()) return multi_step(e, prm, ts, n_steps);
     DevParams P;
     int rc;
     if ((rc = canonicalise(prm, P))) return rc;
-    if (prm->id_count != e->T && e->n > 0)
+    if (e->n_slots == 0) return fail(P3D_ERR_INVALID, "no particles uploaded");
+    if (prm->id_count != e->T)  // (also for an empty upload: the partition kernels index per-type tables of size T)
         return fail(P3D_ERR_INVALID, "id_count %u differs from the uploaded layout (%u): upload again", prm->id_count,
                     e->T);
-    if (e->n_slots == 0) return fail(P3D_ERR_INVALID, "no particles uploaded");
     if (e->world > 1) return fail_sharded(e, "p3d_step");
     CU(cudaSetDevice(e->device));
     return run_steps(e, prm, P, ts, n_steps);
@@ -933,25 +1049,37 @@ int p3d_step(p3d_engine *e, const p3d_params *prm, float ts, int n_steps) {
 
 int p3d_sync(p3d_engine *e) {
     if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    for (p3d_engine *m : e->members) {
+        const int rc = p3d_sync(m);
+        if (rc) return rc;
+    }
+    if (!e->members.empty()) return P3D_OK;
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream));
     return P3D_OK;
 }
 
-int p3d_download(p3d_engine *e, p3d_particle *out, size_t n) {
-    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
-    if (n != e->n) return fail(P3D_ERR_INVALID, "n=%zu but %zu particles are resident", n, e->n);
-    if (n && !out) return fail(P3D_ERR_INVALID, "out is null");
+// Callers [i_begin, i_end) of the resident state -> host (out_part[0] = particle i_begin).
+static int download_range(p3d_engine *e, p3d_particle *out_part, size_t i_begin, size_t i_end, bool sync) {
     CU(cudaSetDevice(e->device));
     int rc;
+    const size_t cnt = i_end - i_begin;
     if (e->opt_timing) {
         if ((rc = ensure_events(e, 1))) return rc;
         CU(cudaEventRecord(e->ev_call[3], e->stream));
     }
-    if ((rc = launch_unpack(e, n))) return rc;
+    if (cnt) {
+        k_unpack<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(e->pos[e->cur].p, e->vel.p,
+                                                                       e->typed ? e->slot_of.p : nullptr, e->aos.p,
+                                                                       (int)i_begin, (int)i_end);
+        e->counters[0]++;
+        CU(cudaGetLastError());
+    }
     if (e->opt_timing) CU(cudaEventRecord(e->ev_call[4], e->stream));
-    if (n) CU(cudaMemcpyAsync(out, e->aos.p, n * sizeof(p3d_particle), cudaMemcpyDeviceToHost, e->stream));
+    if (cnt)
+        CU(cudaMemcpyAsync(out_part, e->aos.p + i_begin * 7, cnt * sizeof(p3d_particle), cudaMemcpyDeviceToHost, e->stream));
     if (e->opt_timing) CU(cudaEventRecord(e->ev_call[5], e->stream));
+    if (!sync) return P3D_OK;
     CU(cudaStreamSynchronize(e->stream));
     if (e->opt_timing) {
         CU(cudaEventElapsedTime(&e->last_ms[3], e->ev_call[3], e->ev_call[4]));
@@ -960,8 +1088,28 @@ int p3d_download(p3d_engine *e, p3d_particle *out, size_t n) {
     return P3D_OK;
 }
 
+int p3d_download(p3d_engine *e, p3d_particle *out, size_t n) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (!e->members.empty()) return multi_download(e, out, n);
+    if (n != e->n) return fail(P3D_ERR_INVALID, "n=%zu but %zu particles are resident", n, e->n);
+    if (n && !out) return fail(P3D_ERR_INVALID, "out is null");
+    return download_range(e, out, 0, n, true);
+}
+
+int p3d_download_part(p3d_engine *e, p3d_particle *out_part, size_t i_begin, size_t i_end) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (!e->members.empty() || e->is_member) return fail(P3D_ERR_INVALID, "p3d_download_part on a multi-device handle: use p3d_download");
+    if (i_begin > i_end || i_end > e->n) return fail(P3D_ERR_INVALID, "bad part [%zu, %zu) of %zu resident particles", i_begin, i_end, e->n);
+    if (i_end > i_begin && !out_part) return fail(P3D_ERR_INVALID, "out is null");
+    return download_range(e, out_part, i_begin, i_end, true);
+}
+
 int p3d_download_render(p3d_engine *e, float world_size, void *out, size_t out_bytes, size_t n) {
     if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (!e->members.empty()) {  // every device holds the whole state after a step
+        int rc = p3d_sync(e);
+        return rc ? rc : p3d_download_render(e->members[0], world_size, out, out_bytes, n);
+    }
     if (n != e->n) return fail(P3D_ERR_INVALID, "n=%zu but %zu particles are resident", n, e->n);
     if (!out || out_bytes < 16 + 32 * n) return fail(P3D_ERR_INVALID, "render buffer needs %zu bytes", 16 + 32 * n);
     // header of WGSL `struct Particles` (src/bin/particles.wgsl:8-12): world_size f32 @0, length u32 @4,
@@ -987,6 +1135,7 @@ int p3d_download_render(p3d_engine *e, float world_size, void *out, size_t out_b
 
 int p3d_download_forces(p3d_engine *e, float *out_xyz, size_t n) {
     if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (!e->members.empty()) return multi_download_forces(e, out_xyz, n);
     if (n != e->n) return fail(P3D_ERR_INVALID, "n=%zu but %zu particles are resident", n, e->n);
     if (!n) return P3D_OK;
     if (!out_xyz) return fail(P3D_ERR_INVALID, "out is null");
@@ -1009,6 +1158,11 @@ int p3d_update(p3d_engine *e, const p3d_params *prm, float ts, const p3d_particl
     if ((rc = canonicalise(prm, P))) return rc;  // src/lib.rs:132 comes first in the reference too
     if (n == 0) return P3D_OK;                   // src/lib.rs:135-171 with an empty Vec is a no-op
     if (!in || !out) return fail(P3D_ERR_INVALID, "in/out is null");
+    if (!e->members.empty()) {
+        if ((rc = multi_upload(e, in, n, prm->id_count))) return rc;
+        if ((rc = multi_step(e, prm, ts, 1))) return rc;
+        return multi_download(e, out, n);
+    }
     if (e->world > 1) return fail_sharded(e, "p3d_update");
     CU(cudaSetDevice(e->device));
     if ((rc = p3d_upload(e, in, n, prm->id_count))) return rc;
@@ -1019,6 +1173,10 @@ int p3d_update(p3d_engine *e, const p3d_params *prm, float ts, const p3d_particl
 
 int p3d_diagnostics(p3d_engine *e, double out[8]) {
     if (!e || !out) return fail(P3D_ERR_INVALID, "null argument");
+    if (!e->members.empty()) {
+        int rc = p3d_sync(e);
+        return rc ? rc : p3d_diagnostics(e->members[0], out);
+    }
     if (e->n_slots == 0) return fail(P3D_ERR_INVALID, "no particles uploaded");
     CU(cudaSetDevice(e->device));
     CU(cudaMemsetAsync(e->diag.p, 0, 8 * sizeof(double), e->stream));
@@ -1033,6 +1191,7 @@ int p3d_diagnostics(p3d_engine *e, double out[8]) {
 
 int p3d_get_timing(p3d_engine *e, float ms[12]) {
     if (!e || !ms) return fail(P3D_ERR_INVALID, "null argument");
+    if (!e->members.empty()) return multi_not_supported("p3d_get_timing");
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream));
     float acc[4] = {0.f, 0.f, 0.f, 0.f};  // partition, pair, rest of force, integrate
@@ -1056,12 +1215,26 @@ int p3d_get_timing(p3d_engine *e, float ms[12]) {
 
 int p3d_get_counters(p3d_engine *e, uint64_t out[4]) {
     if (!e || !out) return fail(P3D_ERR_INVALID, "null argument");
+    if (!e->members.empty()) {  // launches on all devices
+        for (int k = 0; k < 4; ++k) out[k] = 0;
+        for (const p3d_engine *m : e->members)
+            for (int k = 0; k < 4; ++k) out[k] += m->counters[k];
+        return P3D_OK;
+    }
     std::memcpy(out, e->counters, sizeof(e->counters));
     return P3D_OK;
 }
 
 int p3d_device_buffer(p3d_engine *e, int which, void **dev_ptr, size_t *n_slots) {
     if (!e || !dev_ptr) return fail(P3D_ERR_INVALID, "null argument");
+    if (!e->members.empty()) return multi_not_supported("p3d_device_buffer");
+    if (which == P3D_BUF_AOS) {  // staging array of the sharded upload: 7 words per caller index
+        const size_t n = e->n_staged ? e->n_staged : e->n;
+        if (!e->aos.p || n == 0) return fail(P3D_ERR_INVALID, "no particles staged (p3d_upload_part) or uploaded");
+        *dev_ptr = e->aos.p;
+        if (n_slots) *n_slots = staged_part(n, e->world) * (size_t)e->world;
+        return P3D_OK;
+    }
     if (e->n_slots == 0) return fail(P3D_ERR_INVALID, "no particles uploaded");
     switch (which) {
         case P3D_BUF_POS: *dev_ptr = e->pos[e->cur].p; break;
@@ -1077,6 +1250,17 @@ int p3d_device_buffer(p3d_engine *e, int which, void **dev_ptr, size_t *n_slots)
 int p3d_set_shard(p3d_engine *e, int rank, int world) {
     if (!e) return fail(P3D_ERR_INVALID, "engine is null");
     if (world < 1 || rank < 0 || rank >= world) return fail(P3D_ERR_INVALID, "bad shard %d/%d", rank, world);
+    if (!e->members.empty() || e->is_member) return multi_not_supported("p3d_set_shard");
+    if (world != e->world && e->n_slots != 0) {
+        // the slot layout was padded to B * world at upload time: with another world the force / integrate splits
+        // would disagree and the shards become unequal.  The resident state is dropped; upload again.
+        CU(cudaSetDevice(e->device));
+        CU(cudaStreamSynchronize(e->stream));
+        e->n = 0;
+        e->n_slots = 0;
+        e->M = 0;
+        e->layout_version++;
+    }
     e->rank = rank;
     e->world = world;
     return P3D_OK;
@@ -1084,6 +1268,7 @@ int p3d_set_shard(p3d_engine *e, int rank, int world) {
 
 int p3d_shard_range(p3d_engine *e, size_t *slot_begin, size_t *slot_end) {
     if (!e || !slot_begin || !slot_end) return fail(P3D_ERR_INVALID, "null argument");
+    if (!e->members.empty()) return multi_not_supported("p3d_shard_range");
     const int per = ((e->M + e->world - 1) / e->world) * e->B;
     const int s0 = std::min(e->n_slots, e->rank * per);
     *slot_begin = (size_t)s0;
@@ -1093,6 +1278,7 @@ int p3d_shard_range(p3d_engine *e, size_t *slot_begin, size_t *slot_end) {
 
 int p3d_shard_force(p3d_engine *e, const p3d_params *prm) {
     if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (!e->members.empty()) return multi_not_supported("p3d_shard_force");
     DevParams P;
     int rc;
     if ((rc = canonicalise(prm, P))) return rc;
@@ -1109,6 +1295,7 @@ int p3d_shard_force(p3d_engine *e, const p3d_params *prm) {
 
 int p3d_shard_integrate(p3d_engine *e, const p3d_params *prm, float ts) {
     if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (!e->members.empty()) return multi_not_supported("p3d_shard_integrate");
     DevParams P;
     int rc;
     if ((rc = canonicalise(prm, P))) return rc;
@@ -1117,13 +1304,16 @@ int p3d_shard_integrate(p3d_engine *e, const p3d_params *prm, float ts) {
 }
 
 // ---- peer memory for the fused integrate kernel ----
-int p3d_ipc_export(p3d_engine *e, unsigned char *handles /* 3 * 64 bytes */) {
+constexpr int kPeerBufs = 4;  // frc, pos[0], pos[1], vel
+
+int p3d_ipc_export(p3d_engine *e, unsigned char *handles /* 4 * 64 bytes */) {
     if (!e || !handles) return fail(P3D_ERR_INVALID, "null argument");
+    if (!e->members.empty() || e->is_member) return fail(P3D_ERR_INVALID, "a multi-device handle needs no IPC");
     if (e->n_slots == 0) return fail(P3D_ERR_INVALID, "no particles uploaded");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     CU(cudaSetDevice(e->device));
-    void *ptrs[3] = {e->frc.p, e->pos[0].p, e->pos[1].p};
-    for (int k = 0; k < 3; ++k) {
+    void *ptrs[kPeerBufs] = {e->frc.p, e->pos[0].p, e->pos[1].p, e->vel.p};
+    for (int k = 0; k < kPeerBufs; ++k) {
         cudaIpcMemHandle_t h;
         CU(cudaIpcGetMemHandle(&h, ptrs[k]));
         std::memcpy(handles + 64 * k, &h, 64);
@@ -1134,34 +1324,39 @@ int p3d_ipc_export(p3d_engine *e, unsigned char *handles /* 3 * 64 bytes */) {
 
 int p3d_ipc_close(p3d_engine *e) {
     if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (e->is_member) return P3D_OK;  // peer tables of a multi-device handle are plain pointers
     cudaSetDevice(e->device);
     for (int g = 0; g < 8; ++g) {
         if (e->peer_open[g])
-            for (int k = 0; k < 3; ++k)
+            for (int k = 0; k < kPeerBufs; ++k)
                 if (e->peer_ptr[g][k]) cudaIpcCloseMemHandle(e->peer_ptr[g][k]);
         e->peer_open[g] = false;
-        for (int k = 0; k < 3; ++k) e->peer_ptr[g][k] = nullptr;
+        for (int k = 0; k < kPeerBufs; ++k) e->peer_ptr[g][k] = nullptr;
     }
     e->peers_ready = false;
     e->ipc_exported = false;
     return P3D_OK;
 }
 
-int p3d_ipc_import(p3d_engine *e, int world, const unsigned char *all_handles /* world * 3 * 64 bytes */) {
+int p3d_ipc_import(p3d_engine *e, int world, const unsigned char *all_handles /* world * 4 * 64 bytes */) {
     if (!e || !all_handles) return fail(P3D_ERR_INVALID, "null argument");
+    if (!e->members.empty() || e->is_member) return fail(P3D_ERR_INVALID, "a multi-device handle needs no IPC");
     if (world != e->world || world > 8) return fail(P3D_ERR_INVALID, "world %d does not match the shard (%d) or exceeds 8", world, e->world);
     CU(cudaSetDevice(e->device));
+    const bool exported = e->ipc_exported;
     p3d_ipc_close(e);
+    e->ipc_exported = exported;
     for (int g = 0; g < world; ++g) {
         if (g == e->rank) {
             e->peer_ptr[g][0] = e->frc.p;
             e->peer_ptr[g][1] = e->pos[0].p;
             e->peer_ptr[g][2] = e->pos[1].p;
+            e->peer_ptr[g][3] = e->vel.p;
             continue;
         }
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < kPeerBufs; ++k) {
             cudaIpcMemHandle_t h;
-            std::memcpy(&h, all_handles + (size_t)(g * 3 + k) * 64, 64);
+            std::memcpy(&h, all_handles + (size_t)(g * kPeerBufs + k) * 64, 64);
             CU(cudaIpcOpenMemHandle(&e->peer_ptr[g][k], h, cudaIpcMemLazyEnablePeerAccess));
         }
         e->peer_open[g] = true;
@@ -1170,13 +1365,7 @@ int p3d_ipc_import(p3d_engine *e, int world, const unsigned char *all_handles /*
     return P3D_OK;
 }
 
-int p3d_shard_integrate_fused(p3d_engine *e, const p3d_params *prm, float ts) {
-    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
-    if (!e->peers_ready) return fail(P3D_ERR_INVALID, "peer buffers not imported (p3d_ipc_import)");
-    DevParams P;
-    int rc;
-    if ((rc = canonicalise(prm, P))) return rc;
-    CU(cudaSetDevice(e->device));
+static int launch_integrate_fused(p3d_engine *e, const DevParams &P, float ts) {
     const int ns = e->n_slots;
     const int per = ((e->M + e->world - 1) / e->world) * e->B;
     const int s0 = std::min(ns, e->rank * per), s1 = std::min(ns, s0 + per);
@@ -1184,6 +1373,7 @@ int p3d_shard_integrate_fused(p3d_engine *e, const p3d_params *prm, float ts) {
     for (int g = 0; g < 8; ++g) {
         pt.frc[g] = (const float4 *)e->peer_ptr[g][0];
         pt.pos_next[g] = (float4 *)e->peer_ptr[g][1 + (e->cur ^ 1)];
+        pt.vel[g] = (float4 *)e->peer_ptr[g][3];
     }
     if (s1 > s0) {
         k_integrate_fused<<<(s1 - s0 + 255) / 256, 256, 0, e->stream>>>(e->pos[e->cur].p, e->vel.p, pt, e->world, s0, s1,
@@ -1195,11 +1385,248 @@ int p3d_shard_integrate_fused(p3d_engine *e, const p3d_params *prm, float ts) {
     return P3D_OK;
 }
 
+int p3d_shard_integrate_fused(p3d_engine *e, const p3d_params *prm, float ts) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (!e->members.empty()) return fail(P3D_ERR_INVALID, "p3d_shard_* on a multi-device handle: use p3d_step / p3d_update");
+    if (!e->peers_ready) return fail(P3D_ERR_INVALID, "peer buffers not imported (p3d_ipc_import)");
+    DevParams P;
+    int rc;
+    if ((rc = canonicalise(prm, P))) return rc;
+    CU(cudaSetDevice(e->device));
+    return launch_integrate_fused(e, P, ts);
+}
+
 int p3d_shard_commit(p3d_engine *e) {
     if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (!e->members.empty()) return multi_not_supported("p3d_shard_commit");
     e->cur ^= 1;
     e->parity ^= 1;
     return P3D_OK;
 }
 
+
+// Caller index -> slot of the current layout (identity unless the pair kernel's type-grouped layout is active).
+// Lets a test or bench pick particles from every type segment / every rank's slot range.
+int p3d_slot_of(p3d_engine *e, uint32_t *out, size_t n) {
+    if (!e) return fail(P3D_ERR_INVALID, "engine is null");
+    if (!e->members.empty()) e = e->members[0];  // all devices hold the same layout
+    if (n != e->n) return fail(P3D_ERR_INVALID, "n=%zu but %zu particles are resident", n, e->n);
+    if (!n) return P3D_OK;
+    if (!out) return fail(P3D_ERR_INVALID, "out is null");
+    CU(cudaSetDevice(e->device));
+    if (e->typed) {
+        CU(cudaMemcpyAsync(out, e->slot_of.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    } else {
+        for (size_t i = 0; i < n; ++i) out[i] = (uint32_t)i;
+    }
+    return P3D_OK;
+}
+
+// ---- one handle, several devices of one node (p3d_create(devices[], n_dev)) ----
+// One member engine per entry of `devices` (rank g of n_dev); the calling thread drives them all.  The same
+// device may be listed more than once (the members then share it: useful on a one-GPU box, no speed-up).
+int p3d_create_multi(const int *devices, int n_dev, p3d_engine **out) {
+    if (!out) return fail(P3D_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!devices || n_dev < 1 || n_dev > 8) return fail(P3D_ERR_INVALID, "p3d_create_multi needs 1..8 devices");
+    if (n_dev == 1) return p3d_create(devices[0], out);
+    p3d_engine *grp = new p3d_engine();
+    grp->device = devices[0];
+    int rc = P3D_OK;
+    for (int g = 0; g < n_dev && !rc; ++g) {
+        p3d_engine *m = nullptr;
+        rc = p3d_create(devices[g], &m);
+        if (rc) break;
+        m->rank = g;
+        m->world = n_dev;
+        m->is_member = true;
+        grp->members.push_back(m);
+    }
+    // peer access between every pair of distinct devices (k_integrate_fused loads and stores peer memory directly)
+    for (int g = 0; g < n_dev && !rc; ++g) {
+        for (int h = 0; h < n_dev && !rc; ++h) {
+            if (devices[h] == devices[g]) continue;
+            int can = 0;
+            cudaError_t ce = cudaDeviceCanAccessPeer(&can, devices[g], devices[h]);
+            if (ce != cudaSuccess || !can) {
+                cudaGetLastError();
+                rc = fail(P3D_ERR_CUDA, "device %d cannot access device %d's memory (no NVLink / PCIe peer path)", devices[g], devices[h]);
+                break;
+            }
+            cudaSetDevice(devices[g]);
+            ce = cudaDeviceEnablePeerAccess(devices[h], 0);
+            if (ce == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ce = cudaSuccess; }
+            if (ce != cudaSuccess) rc = fail(P3D_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", devices[g], devices[h], cudaGetErrorString(ce));
+        }
+    }
+    // two events per member: the barrier after the force pass and the one after the fused integrate
+    for (int k = 0; k < 2 * n_dev && !rc; ++k) {
+        cudaEvent_t ev = nullptr;
+        cudaSetDevice(devices[k % n_dev]);
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            rc = fail(P3D_ERR_CUDA, "creating the barrier events failed");
+            break;
+        }
+        grp->ev_bar.push_back(ev);
+    }
+    if (rc) {
+        const std::string keep = g_last_error;
+        if (grp->members.empty()) delete grp;
+        else p3d_destroy(grp);  // destroys the members made so far and the handle
+        g_last_error = keep;
+        return rc;
+    }
+    grp->world = n_dev;
+    *out = grp;
+    return P3D_OK;
+}
+
 }  // extern "C"
+
+// Cross-device barrier on the members' streams: every stream continues only after every other stream reached this
+// point.  set = 0 / 1 selects the event set (after the force pass / after the fused integrate).
+static int multi_barrier(p3d_engine *grp, int set) {
+    const int G = (int)grp->members.size();
+    for (int g = 0; g < G; ++g) {
+        CU(cudaSetDevice(grp->members[g]->device));
+        CU(cudaEventRecord(grp->ev_bar[set * G + g], grp->members[g]->stream));
+    }
+    for (int g = 0; g < G; ++g) {
+        CU(cudaSetDevice(grp->members[g]->device));
+        for (int h = 0; h < G; ++h)
+            if (h != g) CU(cudaStreamWaitEvent(grp->members[g]->stream, grp->ev_bar[set * G + h], 0));
+    }
+    return P3D_OK;
+}
+
+static int multi_upload(p3d_engine *grp, const p3d_particle *in, size_t n, uint32_t id_count) {
+    const int G = (int)grp->members.size();
+    int rc;
+    grp->n = 0;
+    grp->n_slots = 0;
+    const size_t per = staged_part(n, G);
+    // every member copies ITS part of the caller's array over its own PCIe link ...
+    for (int g = 0; g < G; ++g) {
+        p3d_engine *m = grp->members[g];
+        CU(cudaSetDevice(m->device));
+        CU(cudaStreamSynchronize(m->stream));  // no step of the previous state may still be reading the buffers
+        const size_t c0 = std::min(n, per * g), c1 = std::min(n, c0 + per);
+        if ((rc = stage_input(m, in ? in + c0 : nullptr, c0, c1, n))) return rc;
+    }
+    // ... and pushes it into every other member's staging array over NVLink (all-gather by peer copies)
+    for (int g = 0; g < G; ++g) {
+        p3d_engine *m = grp->members[g];
+        CU(cudaSetDevice(m->device));
+        const size_t c0 = std::min(n, per * g), c1 = std::min(n, c0 + per);
+        for (int h = 0; h < G && c1 > c0; ++h) {
+            if (h == g) continue;
+            p3d_engine *o = grp->members[h];
+            CU(cudaMemcpyPeerAsync(o->aos.p + c0 * 7, o->device, m->aos.p + c0 * 7, m->device,
+                                   (c1 - c0) * sizeof(p3d_particle), m->stream));
+        }
+    }
+    if ((rc = multi_barrier(grp, 0))) return rc;
+    // every member builds the same layout from the same array; the count kernels of all members run concurrently
+    const bool pair = resolve_force_kernel_for(grp->members[0], n) == P3D_FORCE_PAIR;
+    if (pair)
+        for (int g = 0; g < G; ++g) {
+            CU(cudaSetDevice(grp->members[g]->device));
+            if ((rc = layout_count_async(grp->members[g], n, id_count))) return rc;
+        }
+    for (int g = 0; g < G; ++g) {
+        CU(cudaSetDevice(grp->members[g]->device));
+        if ((rc = upload_commit(grp->members[g], n, id_count, pair))) return rc;
+    }
+    // peer tables: plain pointers (one process, peer access enabled); refreshed because an upload may reallocate
+    for (int g = 0; g < G; ++g) {
+        p3d_engine *m = grp->members[g];
+        for (int h = 0; h < G; ++h) {
+            p3d_engine *o = grp->members[h];
+            m->peer_ptr[h][0] = o->frc.p;
+            m->peer_ptr[h][1] = o->pos[0].p;
+            m->peer_ptr[h][2] = o->pos[1].p;
+            m->peer_ptr[h][3] = o->vel.p;
+        }
+        m->peers_ready = true;
+    }
+    grp->n = n;
+    grp->n_slots = grp->members[0]->n_slots;
+    grp->T = id_count;
+    return P3D_OK;
+}
+
+static int multi_step(p3d_engine *grp, const p3d_params *prm, float ts, int n_steps) {
+    const int G = (int)grp->members.size();
+    DevParams P;
+    int rc;
+    if ((rc = canonicalise(prm, P))) return rc;
+    if (grp->n_slots == 0) return fail(P3D_ERR_INVALID, "no particles uploaded");
+    if (prm->id_count != grp->T)
+        return fail(P3D_ERR_INVALID, "id_count %u differs from the uploaded layout (%u): upload again", prm->id_count, grp->T);
+    for (int g = 0; g < G; ++g) {
+        CU(cudaSetDevice(grp->members[g]->device));
+        if ((rc = upload_matrix(grp->members[g], prm))) return rc;
+    }
+    for (int s = 0; s < n_steps; ++s) {
+        // force pass: every device evaluates its share (block rows / cell-sorted range) -> PARTIAL forces for all slots
+        for (int g = 0; g < G; ++g) {
+            p3d_engine *m = grp->members[g];
+            CU(cudaSetDevice(m->device));
+            // the out-of-box flag written by a member's integrate covers only its own slots
+            if ((rc = check_box_now(m, P))) return rc;
+            if ((rc = launch_force(m, P))) return rc;
+        }
+        if ((rc = multi_barrier(grp, 0))) return rc;  // every device's partial forces are complete
+        // reduce-scatter(forces) + integrate + all-gather(positions, velocities) in one kernel per device
+        for (int g = 0; g < G; ++g) {
+            CU(cudaSetDevice(grp->members[g]->device));
+            if ((rc = launch_integrate_fused(grp->members[g], P, ts))) return rc;
+        }
+        if ((rc = multi_barrier(grp, 1))) return rc;  // every device's peer stores have landed
+        for (int g = 0; g < G; ++g) {
+            grp->members[g]->cur ^= 1;
+            grp->members[g]->parity ^= 1;
+        }
+    }
+    return P3D_OK;
+}
+
+static int multi_download(p3d_engine *grp, p3d_particle *out, size_t n) {
+    const int G = (int)grp->members.size();
+    if (n != grp->n) return fail(P3D_ERR_INVALID, "n=%zu but %zu particles are resident", n, grp->n);
+    if (n && !out) return fail(P3D_ERR_INVALID, "out is null");
+    int rc;
+    const size_t per = staged_part(n, G);
+    // every device holds the whole state; each serves its part of the caller's array over its own PCIe link
+    for (int g = 0; g < G; ++g) {
+        const size_t c0 = std::min(n, per * g), c1 = std::min(n, c0 + per);
+        if ((rc = download_range(grp->members[g], out + c0, c0, c1, false))) return rc;
+    }
+    for (int g = 0; g < G; ++g) {
+        CU(cudaSetDevice(grp->members[g]->device));
+        CU(cudaStreamSynchronize(grp->members[g]->stream));
+    }
+    return P3D_OK;
+}
+
+static int multi_download_forces(p3d_engine *grp, float *out_xyz, size_t n) {
+    const int G = (int)grp->members.size();
+    if (n != grp->n) return fail(P3D_ERR_INVALID, "n=%zu but %zu particles are resident", n, grp->n);
+    if (!n) return P3D_OK;
+    if (!out_xyz) return fail(P3D_ERR_INVALID, "out is null");
+    int rc;
+    if ((rc = p3d_sync(grp))) return rc;
+    p3d_engine *e = grp->members[0];
+    CU(cudaSetDevice(e->device));
+    if ((rc = e->fout.ensure(n * 3))) return rc;
+    PeerForces pf;
+    for (int g = 0; g < 8; ++g) pf.frc[g] = g < G ? grp->members[g]->frc.p : nullptr;
+    k_unpack_forces_sum<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(pf, G, e->typed ? e->slot_of.p : nullptr,
+                                                                            e->fout.p, (int)n);
+    e->counters[0]++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_xyz, e->fout.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return P3D_OK;
+}

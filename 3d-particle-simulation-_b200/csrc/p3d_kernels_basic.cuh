@@ -144,13 +144,14 @@ __global__ void __launch_bounds__(kTypeThreads) k_pack_typed(const float *__rest
     slot_of[base + t] = s;
 }
 
-// K3c: SoA slots -> AoS in the caller's index order (src/lib.rs:268: index order preserved).
+// K3c: SoA slots -> AoS in the caller's index order (src/lib.rs:268: index order preserved), callers
+// [i_begin, i_end) (a multi-GPU run reads every device's part back over its own PCIe link).
 __global__ void __launch_bounds__(256) k_unpack(const float4 *__restrict__ pos, const float4 *__restrict__ vel,
                                                 const uint32_t *__restrict__ slot_of, float *__restrict__ aos,
-                                                int n) {
+                                                int i_begin, int i_end) {
     __shared__ float sm[256 * 7];
-    const int base = blockIdx.x * 256;
-    const int cnt = min(256, n - base);
+    const int base = i_begin + blockIdx.x * 256;
+    const int cnt = min(256, i_end - base);
     const int t = threadIdx.x;
     if (t < cnt) {
         uint32_t s = slot_of ? slot_of[base + t] : (uint32_t)(base + t);
@@ -193,6 +194,28 @@ __global__ void __launch_bounds__(256) k_unpack_forces(const float4 *__restrict_
     if (!P3D_SLOT_OK(s)) return;
     const float4 f = frc[s];
     out[3 * i] = f.x; out[3 * i + 1] = f.y; out[3 * i + 2] = f.z;
+}
+
+// Same for a multi-device handle: every device holds PARTIAL forces, the total is their sum (fixed device order).
+struct PeerForces {
+    const float4 *frc[8];
+};
+__global__ void __launch_bounds__(256) k_unpack_forces_sum(const __grid_constant__ PeerForces peers, int world,
+                                                           const uint32_t *__restrict__ slot_of,
+                                                           float *__restrict__ out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = slot_of ? slot_of[i] : (uint32_t)i;
+    if (!P3D_SLOT_OK(s)) return;
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        if (g < world) {
+            const float4 f = peers.frc[g][s];
+            fx += f.x; fy += f.y; fz += f.z;
+        }
+    }
+    out[3 * i] = fx; out[3 * i + 1] = fy; out[3 * i + 2] = fz;
 }
 
 // Sets flags[0] |= 1 when some particle lies outside [-W/2, W/2]^3.  The fast force kernel assumes
@@ -349,35 +372,48 @@ __global__ void __launch_bounds__(256) k_integrate(const float4 *__restrict__ po
     vel[s] = v;
 }
 
-// K2 fused with its two collectives for one-process-per-GPU runs (NVLink peer memory):
+// K2 fused with its two collectives for multi-GPU runs (NVLink peer memory):
 //   reduce-scatter : the total force on an owned slot is the sum of every rank's partial force,
 //                    read straight from the peers' force buffers (P2P loads);
 //   integrate      : src/lib.rs:245-264, as k_integrate;
-//   all-gather     : the new position is stored into every rank's next-position buffer (P2P stores).
-// peers.frc[g] / peers.pos_next[g] are device pointers into rank g's memory (cudaIpcOpenMemHandle);
-// entry `rank` is the local buffer.  The driver separates force pass, this kernel and the next force
-// pass with a cross-rank barrier.
+//   all-gather     : the new position AND velocity are stored into every rank's buffers (P2P stores), so that
+//                    every rank holds the whole state after the step (any rank can then serve any part of the
+//                    caller's array, src/lib.rs:268-271).
+// peers.frc[g] / pos_next[g] / vel[g] are device pointers into rank g's memory (cudaIpcOpenMemHandle, or plain
+// peer access inside a multi-device handle); entry `rank` is the local buffer.  The driver separates force
+// pass, this kernel and the next force pass with a cross-rank barrier.
 struct PeerTable {
     const float4 *frc[8];
     float4 *pos_next[8];
+    float4 *vel[8];
 };
 
-__global__ void __launch_bounds__(256) k_integrate_fused(const float4 *__restrict__ pos, float4 *__restrict__ vel,
-                                                         PeerTable peers, int world, int s_begin, int s_end,
-                                                         DevParams P, float ts, int *__restrict__ flag_next) {
+__global__ void __launch_bounds__(256) k_integrate_fused(const float4 *__restrict__ pos, const float4 *vel_own,
+                                                         const __grid_constant__ PeerTable peers, int world, int s_begin,
+                                                         int s_end, DevParams P, float ts, int *__restrict__ flag_next) {
     const int s = s_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= s_end) return;
     float4 p = pos[s];
     if (f2u(p.w) == P3D_GHOST_ID) return;
     float4 F = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int g = 0; g < world; ++g) {  // fixed rank order: every run sums identically
-        const float4 f = peers.frc[g][s];
-        F.x += f.x; F.y += f.y; F.z += f.z;
+    // fixed rank order: every run sums identically.  Fully unrolled with a guard so that the pointer table is
+    // read from the constant bank with immediate offsets (a runtime index would force a stack copy).
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        if (g < world) {
+            const float4 f = peers.frc[g][s];
+            F.x += f.x; F.y += f.y; F.z += f.z;
+        }
     }
-    float4 v = vel[s];
+    float4 v = vel_own[s];
     if (!integrate_particle(p, v, F, P, ts)) atomicOr(flag_next, 1);
-    for (int g = 0; g < world; ++g) peers.pos_next[g][s] = p;
-    vel[s] = v;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        if (g < world) {
+            peers.pos_next[g][s] = p;
+            peers.vel[g][s] = v;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

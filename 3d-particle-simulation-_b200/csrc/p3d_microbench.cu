@@ -1,4 +1,5 @@
-// p3d_microbench.cu — FP32-pipe microbenchmarks.  They measure what one SM sub-partition can
+// p3d_microbench.cu — FP32-pipe microbenchmarks (own library, libp3d_microbench.so: measurement
+// infrastructure, not linked into the product libp3d.so).  They measure what one SM sub-partition can
 // issue per clock for the instruction kinds the force kernel is made of, so that the roofline
 // denominator (148 SMs x 128 lanes x clock) and the packed-FP32 assumption are checked on the
 // actual device instead of taken from a data sheet.
@@ -6,7 +7,8 @@
 
 #include <cstdio>
 
-#include "p3d.h"
+#include "p3d.h"  // error codes only
+#include "p3d_microbench.h"
 
 namespace {
 

@@ -11,6 +11,7 @@
 // here the same conditions throw particle_3d::Panic carrying the engine's message.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -51,7 +52,14 @@ class Particles {
     float particle_effect_radius = 2.0f;
     bool walls = false;
     Vector3 acceleration;
+    // Not a field of the reference: true reproduces its bucket double-visit quirk (P3D_OPT_FAITHFUL; SURVEY.md
+    // Appendix B.1).  The default evaluates every in-range pair exactly once, which DEVIATES from
+    // src/lib.rs:195-206 for the ~26*k/N of the particles whose 27 hashed cells collide modulo N per step.
+    // The environment variable P3D_FAITHFUL=1 flips the default.
+    bool faithful = env_flag("P3D_FAITHFUL");
 
+    // device >= 0: that CUDA device.  The environment variable P3D_DEVICES="0,1,2,3" overrides device 0 with a
+    // list: one engine handle then drives all of them (p3d_create_multi) behind the unchanged update().
     explicit Particles(int device = 0) : device_(device) {}
     Particles(const Particles &) = delete;
     Particles &operator=(const Particles &) = delete;
@@ -86,6 +94,7 @@ class Particles {
         if (attraction_matrix.size() < (size_t)id_count * id_count)
             throw Panic(P3D_ERR_BAD_ID, "attraction_matrix shorter than id_count^2 (src/lib.rs:225-228)");
         ensure_engine();
+        check(p3d_set_option(engine_, P3D_OPT_FAITHFUL, faithful ? 1 : 0));
         const p3d_params prm = params();
         std::vector<Particle> next(active_particles.size());
         const int rc = p3d_update(engine_, &prm, ts, reinterpret_cast<const p3d_particle *>(active_particles.data()),
@@ -100,6 +109,7 @@ class Particles {
     // download (the per-step host round trip of update() is what main.rs:199 + :445 would pay).
     void run(float ts, int n_steps) {
         ensure_engine();
+        check(p3d_set_option(engine_, P3D_OPT_FAITHFUL, faithful ? 1 : 0));
         const p3d_params prm = params();
         check(p3d_upload(engine_, reinterpret_cast<const p3d_particle *>(active_particles.data()),
                          active_particles.size(), id_count));
@@ -133,8 +143,24 @@ class Particles {
     static void check(int rc) {
         if (rc != P3D_OK) throw Panic(rc, p3d_last_error());
     }
+    static bool env_flag(const char *name) {
+        const char *v = std::getenv(name);
+        return v && *v && !(v[0] == '0' && v[1] == 0);
+    }
     void ensure_engine() {
-        if (!engine_) check(p3d_create(device_, &engine_));
+        if (engine_) return;
+        std::vector<int> devs;
+        if (const char *env = (device_ == 0) ? std::getenv("P3D_DEVICES") : nullptr) {
+            for (const char *p = env; *p;) {
+                char *end = nullptr;
+                const long d = std::strtol(p, &end, 10);
+                if (end == p) break;
+                devs.push_back((int)d);
+                p = (*end == ',') ? end + 1 : end;
+            }
+        }
+        if (devs.size() > 1) check(p3d_create_multi(devs.data(), (int)devs.size(), &engine_));
+        else check(p3d_create(devs.empty() ? device_ : devs[0], &engine_));
     }
     int device_ = 0;
     p3d_engine *engine_ = nullptr;

@@ -13,6 +13,7 @@ reads like the Rust `Vec<Particle>`.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -35,10 +36,19 @@ def Particle(position=(0.0, 0.0, 0.0), velocity=(0.0, 0.0, 0.0), id=0):  # noqa:
 class Engine:
     """Thin RAII wrapper over p3d_engine* (device-resident stepping, options, timing)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """device: one CUDA device index, or a list of 2..8 indices of one node (p3d_create_multi: one handle drives
+        them all from this thread; p3d_update / step / download work unchanged)."""
         self._lib = _abi.load()
         h = C.c_void_p()
-        _abi.check(self._lib.p3d_create(device, C.byref(h)))
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*[int(d) for d in device])
+            _abi.check(self._lib.p3d_create_multi(devs, len(device), C.byref(h)))
+            self.devices = [int(d) for d in device]
+            device = self.devices[0]
+        else:
+            _abi.check(self._lib.p3d_create(device, C.byref(h)))
+            self.devices = [int(device)]
         self._h = h
         self.device = device
         self._n = 0
@@ -111,6 +121,27 @@ class Engine:
         if out.dtype != PARTICLE or out.shape[0] != self._n or not out.flags["C_CONTIGUOUS"]:
             raise ValueError(f"out must be a contiguous PARTICLE array of {self._n} entries")
         _abi.check(self._lib.p3d_download(self._h, out.ctypes.data, self._n))
+
+    def upload_part(self, part: np.ndarray, i_begin: int, n: int, id_count: int):
+        """Sharded upload, phase 1: this rank's callers [i_begin, i_begin + len(part)) of n -> the staging array."""
+        inp = np.ascontiguousarray(part, dtype=PARTICLE)
+        _abi.check(self._lib.p3d_upload_part(self._h, inp.ctypes.data, i_begin, i_begin + inp.shape[0], n, id_count))
+
+    def upload_commit(self, n: int):
+        """Sharded upload, phase 2 (after the driver all-gathered BUF_AOS): layout + pack."""
+        _abi.check(self._lib.p3d_upload_commit(self._h))
+        self._n = n
+
+    def download_part_into(self, out: np.ndarray, i_begin: int):
+        if out.dtype != PARTICLE or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a contiguous PARTICLE array")
+        _abi.check(self._lib.p3d_download_part(self._h, out.ctypes.data, i_begin, i_begin + out.shape[0]))
+
+    def slot_of(self) -> np.ndarray:
+        """Caller index -> slot of the resident layout."""
+        out = np.empty(self._n, dtype=np.uint32)
+        _abi.check(self._lib.p3d_slot_of(self._h, out.ctypes.data, self._n))
+        return out
 
     def download_forces(self) -> np.ndarray:
         out = np.zeros((self._n, 3), dtype=np.float32)
@@ -188,12 +219,12 @@ class Engine:
         _abi.check(self._lib.p3d_shard_integrate_fused(self._h, C.byref(params), ts))
 
     def ipc_export(self) -> bytes:
-        buf = C.create_string_buffer(3 * 64)
+        buf = C.create_string_buffer(_abi.IPC_HANDLES * 64)
         _abi.check(self._lib.p3d_ipc_export(self._h, buf))
         return buf.raw
 
     def ipc_import(self, world: int, all_handles: bytes):
-        assert len(all_handles) == world * 3 * 64
+        assert len(all_handles) == world * _abi.IPC_HANDLES * 64
         _abi.check(self._lib.p3d_ipc_import(self._h, world, all_handles))
 
     def ipc_close(self):
@@ -219,7 +250,15 @@ class Particles:
         self.particle_effect_radius = particle_effect_radius
         self.walls = walls
         self.acceleration = tuple(acceleration)
-        self._device = device
+        # P3D_DEVICES="0,1,2,3": one engine handle over several GPUs of the node (p3d_create_multi)
+        env = os.environ.get("P3D_DEVICES", "").strip()
+        self._device = [int(d) for d in env.split(",")] if env and device == 0 else device
+        if isinstance(self._device, list) and len(self._device) == 1:
+            self._device = self._device[0]
+        # faithful = True reproduces the reference's bucket double-visit quirk (P3D_OPT_FAITHFUL).
+        # The default (False, or P3D_FAITHFUL=1 in the environment to flip it) evaluates every in-range pair exactly
+        # once, which DEVIATES from src/lib.rs:195-206 for the ~26*k/N of the particles whose 27 hashed cells collide.
+        self.faithful = os.environ.get("P3D_FAITHFUL", "0") not in ("", "0")
         self._engine = None
 
     @property
@@ -241,6 +280,7 @@ class Particles:
         pre-step state (src/lib.rs:167) and `active_particles` the post-step state in the same
         index order; the return value is a copy of it (src/lib.rs:271).
         """
+        self.engine.set_option(_abi.OPT_FAITHFUL, 1 if self.faithful else 0)
         new = self.engine.update(self._params(), ts, self.active_particles)
         self.past_particles = self.active_particles  # src/lib.rs:167 swap
         self.active_particles = new
@@ -252,6 +292,7 @@ def _particles_run(self, ts: float, n_steps: int) -> np.ndarray:
     wants.  Equivalent to calling update() n_steps times; past_particles is the state before the LAST step
     only when n_steps == 1, otherwise it is the state before the run."""
     eng = self.engine
+    eng.set_option(_abi.OPT_FAITHFUL, 1 if self.faithful else 0)
     before = self.active_particles
     eng.upload(before, self.id_count)
     eng.step(self._params(), ts, n_steps)

@@ -21,7 +21,8 @@ MAX_TYPES = 64
 # options
 OPT_FORCE_KERNEL, OPT_TIMING, OPT_GRAPH, OPT_BLOCK_SORT, OPT_BLOCK_SIZE, OPT_FAITHFUL = 0, 1, 2, 3, 4, 5
 FORCE_AUTO, FORCE_REFERENCE_ORDER, FORCE_PAIR, FORCE_CELLS = 0, 1, 2, 3
-BUF_POS, BUF_POS_NEXT, BUF_VEL, BUF_FORCE = 0, 1, 2, 3
+BUF_POS, BUF_POS_NEXT, BUF_VEL, BUF_FORCE, BUF_AOS = 0, 1, 2, 3, 4
+IPC_HANDLES = 4  # P3D_IPC_HANDLES: force, both position buffers, velocities
 
 # p3d_particle: 28 bytes (src/lib.rs:12-17)
 PARTICLE = np.dtype(
@@ -52,8 +53,9 @@ EXPORTS = [
     "p3d_get_timing", "p3d_get_counters", "p3d_set_stream", "p3d_device_buffer", "p3d_set_shard",
     "p3d_shard_range", "p3d_shard_force", "p3d_shard_integrate", "p3d_shard_commit",
     "p3d_ipc_export", "p3d_ipc_import", "p3d_ipc_close", "p3d_shard_integrate_fused",
-    "p3d_scene_default_params", "p3d_scene_uniform", "p3d_scene_plummer", "p3d_microbench",
+    "p3d_scene_default_params", "p3d_scene_uniform", "p3d_scene_plummer",
     "p3d_debug_bounds_violations",
+    "p3d_create_multi", "p3d_slot_of", "p3d_upload_part", "p3d_upload_commit", "p3d_download_part",
 ]
 
 _lib = None
@@ -129,8 +131,16 @@ def load():
     L.p3d_scene_uniform.argtypes = [C.c_uint64, sz, f32, C.c_uint32, vp]
     L.p3d_scene_plummer.restype = None
     L.p3d_scene_plummer.argtypes = [C.c_uint64, sz, f32, f32, C.c_uint32, vp]
-    L.p3d_microbench.restype = i32
-    L.p3d_microbench.argtypes = [i32, i32, i32, C.POINTER(C.c_double)]
+    L.p3d_create_multi.restype = i32
+    L.p3d_create_multi.argtypes = [C.POINTER(i32), i32, C.POINTER(vp)]
+    L.p3d_slot_of.restype = i32
+    L.p3d_slot_of.argtypes = [vp, vp, sz]
+    L.p3d_upload_part.restype = i32
+    L.p3d_upload_part.argtypes = [vp, vp, sz, sz, sz, C.c_uint32]
+    L.p3d_upload_commit.restype = i32
+    L.p3d_upload_commit.argtypes = [vp]
+    L.p3d_download_part.restype = i32
+    L.p3d_download_part.argtypes = [vp, vp, sz, sz]
     L.p3d_debug_bounds_violations.restype = i32
     L.p3d_debug_bounds_violations.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     _lib = L

@@ -44,7 +44,8 @@ def engine_tensors(engine, device_index: int):
     import torch
 
     out = {}
-    for name, which in (("pos", _abi.BUF_POS), ("pos_next", _abi.BUF_POS_NEXT), ("force", _abi.BUF_FORCE)):
+    for name, which in (("pos", _abi.BUF_POS), ("pos_next", _abi.BUF_POS_NEXT), ("force", _abi.BUF_FORCE),
+                        ("vel", _abi.BUF_VEL)):
         ptr, n = engine.device_buffer(which)
         out[name] = torch.as_tensor(_CudaView(ptr, n), device=f"cuda:{device_index}")
     return out
@@ -71,6 +72,16 @@ class ShardedStepper:
         # collective left is a one-element all-reduce used as a stream-ordered cross-rank barrier
         self.fused = fused and world > 1
         self._bar = barrier_tensor
+        # The collectives run on torch's current stream: the engine's kernels must be on the same stream, otherwise
+        # the force all-reduce / the fused kernel's peer reads race with them.  (CPU stand-ins have no streams.)
+        if hasattr(engine, "set_stream"):
+            try:
+                import torch
+
+                if torch.cuda.is_available():
+                    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+            except ImportError:
+                pass
 
     def reset(self):
         """Call after a re-upload: the engine starts again from its first position buffer."""
@@ -103,9 +114,43 @@ class ShardedStepper:
                 s0, s1 = eng.shard_range()
                 # the send shard is copied first: not every backend accepts an input that aliases the output
                 dist.all_gather_into_tensor(t["pos_next"], t["pos_next"][s0:s1].clone())
+                # velocities too, so that every rank holds the whole state (any rank can download any part)
+                if "vel" in t:
+                    dist.all_gather_into_tensor(t["vel"], t["vel"][s0:s1].clone())
+                    self.collectives += 1
                 self.collectives += 1
             eng.shard_commit()
             self._parity ^= 1
+
+
+def part_range(n: int, rank: int, world: int):
+    """Callers [begin, end) rank `rank` moves over its own PCIe link (equal parts of ceil(n / world))."""
+    per = (n + world - 1) // world
+    c0 = min(n, per * rank)
+    return c0, min(n, c0 + per)
+
+
+def sharded_upload(engine, dist, rank: int, world: int, device_index: int, particles, id_count: int):
+    """Every rank copies only its 1/world of `particles` (a host array all ranks hold, or hold their part of) to its
+    GPU, the staging arrays are all-gathered over NVLink, then every rank builds the layout.  Replaces `world` full
+    host-to-device copies of the same array."""
+    import torch
+
+    n = particles.shape[0]
+    c0, c1 = part_range(n, rank, world)
+    engine.upload_part(particles[c0:c1], c0, n, id_count)
+    if world > 1:
+        ptr, cap = engine.device_buffer(_abi.BUF_AOS)
+        per = cap // world
+
+        class _V:
+            __cuda_array_interface__ = {"shape": (cap * 7,), "typestr": "<f4", "data": (ptr, False), "version": 2,
+                                        "strides": None}
+
+        t = torch.as_tensor(_V(), device=f"cuda:{device_index}")
+        dist.all_gather_into_tensor(t, t[rank * per * 7:(rank + 1) * per * 7].clone())
+        torch.cuda.current_stream().synchronize()  # the layout kernels may run on another stream than the collective
+    engine.upload_commit(n)
 
 
 def shard_slot_range(n_blocks: int, block: int, rank: int, world: int):

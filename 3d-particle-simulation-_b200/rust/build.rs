@@ -10,7 +10,7 @@ fn main() {
     let root = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("p3d");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     let cuda_lib = env::var("CUDA_LIB_DIR").unwrap_or_else(|_| "/usr/local/cuda/lib64".into());
-    let srcs = ["csrc/p3d_engine.cu", "csrc/p3d_microbench.cu", "csrc/p3d_scene.cpp"];
+    let srcs = ["csrc/p3d_engine.cu", "csrc/p3d_scene.cpp"];
     let mut objs = Vec::new();
     for s in srcs {
         let obj = out.join(format!("{}.o", s.replace('/', "_")));

@@ -42,6 +42,20 @@ impl Drop for Engine {
 }
 thread_local! { static ENGINE: RefCell<Option<Engine>> = const { RefCell::new(None) }; }
 
+/// Devices the engine runs on: `P3D_DEVICES="0,1,2,3"` (one handle drives them all), default device 0.
+fn devices_from_env() -> Vec<i32> {
+    std::env::var("P3D_DEVICES").ok()
+        .map(|s| s.split(',').filter_map(|d| d.trim().parse().ok()).collect::<Vec<i32>>())
+        .filter(|v| !v.is_empty()).unwrap_or_else(|| vec![0])
+}
+
+/// `P3D_FAITHFUL=1`: reproduce the reference's bucket double-visit quirk (two of the 27 hashed cells colliding
+/// modulo N scan a bucket twice, src/lib.rs:195-206).  The default evaluates every in-range pair exactly once,
+/// which deviates from the reference for the ~26*k/N of the particles per step that the quirk touches.
+fn faithful_from_env() -> bool {
+    std::env::var("P3D_FAITHFUL").map(|v| !v.is_empty() && v != "0").unwrap_or(false)
+}
+
 fn last_error() -> String {
     unsafe { CStr::from_ptr(ffi::p3d_last_error()).to_string_lossy().into_owned() }
 }
@@ -72,7 +86,13 @@ impl Particles {
             let mut slot = cell.borrow_mut();
             if slot.is_none() {
                 let mut raw = std::ptr::null_mut();
-                let rc = unsafe { ffi::p3d_create(0, &mut raw) };
+                let devs = devices_from_env();
+                let rc = unsafe {
+                    if devs.len() > 1 { ffi::p3d_create_multi(devs.as_ptr(), devs.len() as i32, &mut raw) }
+                    else { ffi::p3d_create(devs[0], &mut raw) }
+                };
+                if rc != 0 { return rc; }
+                let rc = unsafe { ffi::p3d_set_option(raw, ffi::P3D_OPT_FAITHFUL, faithful_from_env() as i32) };
                 if rc != 0 { return rc; }
                 *slot = Some(Engine(raw));
             }

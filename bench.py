@@ -179,7 +179,17 @@ def measured_peaks():
         return None
 
 
-def workload(n: int, W: float, cloud: str = "uniform"):
+def workload(n: int, W: float, cloud: str = "uniform", impl: str = "engine"):
+    """Seeded inputs.  The engine arm uses the product's generator (p3d_scene_*), the reference arm the oracle's own
+    restatement of it (byte-identical: tests/test_oracle_scene.py), so that `--impl reference` never loads libp3d.so."""
+    if impl == "reference":
+        from oracle import oracle as O
+
+        prm = O.default_params_dict()
+        prm["world_size"] = W
+        if cloud == "plummer":
+            return prm, O.scene_plummer(W, n, W / 6, seed=SEED)
+        return prm, O.scene_uniform(W, n, seed=SEED)
     import particle_3d as p3
 
     prm = p3.default_params_dict()
@@ -189,15 +199,33 @@ def workload(n: int, W: float, cloud: str = "uniform"):
     return prm, p3.generate_particles(W, n, seed=SEED)
 
 
-def config_dict(n, W, extra=None, cloud="uniform"):
+def config_dict(n, W, cloud="uniform", weak=False):
+    """Identical in both arms (the driver compares the two dicts): the workload only, nothing about how it is run."""
     what = "uniform cloud" if cloud == "uniform" else "clustered (Plummer a=W/6) cloud"
     c = {"workload": f"N={n} {what}, W={W} (density 1), default scene constants (main.rs:133-148), ts=1/60, seed {SEED}; "
                      "BASELINE.json configs[3]",
          "n_particles": n, "world_size": W, "cloud": cloud, "algorithm": "all-pairs (N^2 ordered pairs per step)",
          "cache": "state is ~100 MB (< L2), so a 512 MiB buffer is overwritten between timed steps to flush L2"}
-    if extra:
-        c.update(extra)
+    if weak:
+        c["weak_scaling"] = ("N = 1,048,576 * sqrt(GPUs) (BASELINE.json configs[4]): the pair count per GPU is that of "
+                             "the 1-GPU run")
     return c
+
+
+PARITY_TOL = 1e-5      # north_star: relative tolerance after one step (floors as in tests/helpers.py)
+PARITY_SAMPLE = 16384  # particles compared with the oracle, drawn from every rank's slot range
+
+
+def parity_sample_errors(out_sample, ref_sample, world_size):
+    """tests/helpers.py parity metric on a sample: |dv| / max(|v|, v_rms), |dp| / max(|p|, W/2), both over PARITY_TOL."""
+    def v3(a, k):
+        return np.stack([a[k + "x"], a[k + "y"], a[k + "z"]], 1).astype(np.float64)
+
+    v, vr, p, pr = v3(out_sample, "v"), v3(ref_sample, "v"), v3(out_sample, "p"), v3(ref_sample, "p")
+    vrms = float(np.sqrt((vr ** 2).sum(1).mean())) if len(vr) else 0.0
+    dv = np.linalg.norm(v - vr, axis=1) / np.maximum(np.linalg.norm(vr, axis=1), max(vrms, 1e-30))
+    dp = np.linalg.norm(p - pr, axis=1) / np.maximum(np.linalg.norm(pr, axis=1), world_size / 2)
+    return float(dv.max() / PARITY_TOL), float(dp.max() / PARITY_TOL)
 
 
 # ------------------------------------------------------------------------------------------
@@ -238,7 +266,7 @@ def run_reference(args):
     if rank != 0:
         return
     n, W = args.n, args.world_size
-    prm, parts = workload(n, W, args.cloud)
+    prm, parts = workload(n, W, args.cloud, impl="reference")
     per_step_budget = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     times, last = [], None
     for s in range(args.warmup + args.steps):
@@ -251,9 +279,10 @@ def run_reference(args):
                   f"particles, scaled by N/sample (faithful mode, {last['cores']} OpenMP threads)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(n, W, cloud=args.cloud),
-        "steps_per_s": 1.0 / step_s,
+        "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "weak" if args.weak else "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(n, W, args.cloud, args.weak),
+        "steps_per_s": 1.0 / step_s, "cpu_cores": last["cores"],
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": sample_txt,
                          "ms_per_step": step_s * 1e3,
                          "candidate_pairs_per_s": last["candidates_per_particle"] * n / step_s},
@@ -270,7 +299,7 @@ def run_engine(args):
 
     import particle_3d as p3
     from particle_3d import _abi
-    from particle_3d.sharded import ShardedStepper, engine_tensors, exchange_peer_handles
+    from particle_3d.sharded import ShardedStepper, engine_tensors, exchange_peer_handles, part_range, sharded_upload
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -370,14 +399,61 @@ def run_engine(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "force_kernel": "k_force_pair: all N^2 pairs (north_star); the cell list is reported separately",
-        "config": config_dict(n, W, {"parallelism": (f"block rows sharded over {world} GPUs; " + ("per step ONE fused kernel does reduce-scatter(forces) + integrate + all-gather(positions) over NVLink peer memory, NCCL only as two 4-byte barrier all-reduces" if fused else "per step all-reduce(forces) + all-gather(positions) over NCCL")) if world > 1 else "1 GPU",
-                                     "block": args.block,
-                                     **({"weak_scaling": "N = 1,048,576 * sqrt(GPUs) (BASELINE.json configs[4]): the pair count per GPU is that of the 1-GPU run"} if args.weak else {})},
-                                    cloud=args.cloud),
+        "config": config_dict(n, W, args.cloud, args.weak),
+        "engine": {"parallelism": (f"block rows sharded over {world} GPUs; " + ("per step ONE fused kernel does reduce-scatter(forces) + integrate + all-gather(positions, velocities) over NVLink peer memory, NCCL only as two 4-byte barrier all-reduces" if fused else "per step all-reduce(forces) + all-gather(positions, velocities) over NCCL")) if world > 1 else "1 GPU",
+                   "block": args.block},
         "steps_per_s": 1e3 / ms_per_step,
         "gpu_launches": int(launches),
         "clocks": clock_summary,
     }
+
+    # ---------------- parity of THIS run's path against the CPU oracle (outside the timed region) ----------------
+    # Re-upload the seed-42 state, take ONE step through the same (sharded) path the timed region used, download,
+    # and compare a sample drawn from every rank's slot range with the oracle (ideal mode; src/lib.rs:167-171,
+    # 268-271: same index order, same state).  A broken peer pointer or a stale barrier would leave every timing
+    # unchanged; this is what catches it.  The run FAILS (exit code 1) when the sample is out of tolerance.
+    def reupload(src):
+        if world > 1:
+            sharded_upload(eng, dist, rank, world, local, src, prm["id_count"])
+            stepper.reset()
+        else:
+            eng.upload(src, prm["id_count"])
+
+    eng.set_option(_abi.OPT_TIMING, 0)
+    reupload(parts)
+    one_step()
+    torch.cuda.synchronize()
+    state = eng.download()  # every rank holds the whole state after a step
+    parity = None
+    digest = __import__("hashlib").sha256(state.tobytes()).hexdigest()
+    digests = [digest]
+    if world > 1:
+        digests = [None] * world
+        dist.all_gather_object(digests, digest)
+    if rank == 0 and not args.no_parity:
+        from oracle import oracle as O
+
+        slot = eng.slot_of().astype(np.int64)
+        s0, s1 = eng.shard_range()
+        owner = slot // max(1, s1 - s0)
+        rng = np.random.default_rng(20261018)
+        per_rank = max(1, PARITY_SAMPLE // world)
+        idx = np.concatenate([rng.choice(np.flatnonzero(owner == g), size=min(per_rank, int((owner == g).sum())), replace=False)
+                              for g in range(world) if (owner == g).any()])
+        t0 = time.perf_counter()
+        ref, _ = O.update_indices(prm, TS, parts, idx, mode=O.IDEAL, nthreads=host_threads())
+        dv, dp = parity_sample_errors(state[idx], ref, W)
+        parity = {"max_dv_over_tol": dv, "max_dp_over_tol": dp, "n_checked": int(idx.size), "mode": "ideal", "tol": PARITY_TOL,
+                  "ranks_covered": sorted(int(g) for g in np.unique(owner[idx])),
+                  "ids_and_order_exact": bool(np.array_equal(state["id"], parts["id"])),
+                  "replicas_identical": len(set(digests)) == 1,
+                  "what": f"one step from the seed-{SEED} state through the timed path; {idx.size} particles drawn from every rank's "
+                          "slot range vs oracle.update_indices (CPU restatement of src/lib.rs, ideal mode); every rank's "
+                          "downloaded copy of the whole state must be byte-identical",
+                  "oracle_s": time.perf_counter() - t0}
+        parity["ok"] = bool(dv <= 1.0 and dp <= 1.0 and parity["ids_and_order_exact"] and parity["replicas_identical"]
+                            and len(parity["ranks_covered"]) == world)
+        line["parity"] = parity
 
     if world == 1 and rank == 0:
         # ---------------- roofline of the dominant kernel (k_force_pair) ----------------
@@ -385,9 +461,8 @@ def run_engine(args):
         peaks = measured_peaks()
         sm_max_mhz = (peaks or {}).get("sm_max_mhz") or clock_summary.get("sm_max_mhz") or 1965.0
         fp32_peak_tf = prop.multi_processor_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
-        import ctypes as C
-        mb = (C.c_double * 4)()
-        _abi.load().p3d_microbench(local, 1, 2000, mb)  # packed FFMA2 microbenchmark
+        from tools import microbench
+        _, mb = microbench.run(local, 1, 2000)  # packed FFMA2 microbenchmark (libp3d_microbench.so)
         force_ms = kern["force"] / max(1, kern["steps"])
         pair_ms = kern["pair"] / max(1, kern["steps"])
         integ_ms = kern["integrate"] / max(1, kern["steps"])
@@ -406,6 +481,10 @@ def run_engine(args):
                            "tensor/HBM peaks do not bound this kernel (not a dense contraction)",
             "peak_ffma2_microbench_tflops": mb[0] * 2 / 1e12,
             "algorithmic_flops_per_launch": flops, "flop_per_interaction": FLOP_PER_INTERACTION,
+            "frac_note": "`frac` follows north_star's 20-flop-per-ordered-interaction convention.  The kernel evaluates each "
+                         "unordered pair once and EXECUTES 16 FP32 flop (8 lane-FMAs) per ordered interaction, so the executed "
+                         "fraction of the FMA peak is frac * 16/20; ncu's measured FMA-pipe utilisation is under `ncu`",
+            "frac_executed_flops": achieved_tf / fp32_peak_tf * 16.0 / 20.0,
             "kernel_ms": force_ms, "pair_kernel_ms": pair_ms, "bxb_tail_ms": kern["bxb"] / max(1, kern["steps"]),
             "bxb_note": "k_force_bxb runs BESIDE k_force_pair on an auxiliary stream (alone, under ncu: 2.2 ms = 0.7 % of the step, "
                         "profiles/r01_launches_n1048576.csv); pair_kernel_ms therefore contains it and bxb_tail_ms is only what "
@@ -473,20 +552,44 @@ def run_engine(args):
                        "d2h_bytes_per_step": n * 28, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                        "api": "p3d_update(engine, params, ts, in, out, n) on pinned host arrays; wall clock around the synchronous call"}
     else:
-        # multi-GPU e2e: every step uploads the full state from pinned host memory on every rank and
-        # reads the rank's shard back (the host mirror would do exactly this per update()).
-        hin = torch.empty(n * 28, dtype=torch.uint8).pin_memory()
-        hout = torch.empty(n * 28, dtype=torch.uint8).pin_memory()
-        a_in = hin.numpy().view(_abi.PARTICLE)
-        a_out = hout.numpy().view(_abi.PARTICLE)
-        a_in[:] = parts
+        # multi-GPU e2e: the caller's array is split over the ranks.  Every step each rank uploads ITS 1/G of the
+        # state from pinned host memory over its own PCIe link, the staging arrays are all-gathered over NVLink, the
+        # type-grouped layout is rebuilt, one sharded step runs, and each rank reads ITS 1/G of the result back.
+        c0, c1 = part_range(n, rank, world)
+        hin = torch.empty(max(1, c1 - c0) * 28, dtype=torch.uint8).pin_memory()
+        hout = torch.empty(max(1, c1 - c0) * 28, dtype=torch.uint8).pin_memory()
+        a_in = hin.numpy().view(_abi.PARTICLE)[:c1 - c0]
+        a_out = hout.numpy().view(_abi.PARTICLE)[:c1 - c0]
+        a_in[:] = parts[c0:c1]
+
+        def e2e_step():
+            eng.upload_part(a_in, c0, n, prm["id_count"])
+            ptr, cap = eng.device_buffer(_abi.BUF_AOS)
+            t = aos_view(ptr, cap)
+            per = cap // world
+            dist.all_gather_into_tensor(t, t[rank * per * 7:(rank + 1) * per * 7].clone())
+            eng.upload_commit(n)
+            stepper.reset()
+            stepper.step(P, TS, 1)
+            eng.download_part_into(a_out, c0)
+
+        aos_cache = {}
+
+        def aos_view(ptr, cap):
+            if (ptr, cap) not in aos_cache:
+                class _V:
+                    __cuda_array_interface__ = {"shape": (cap * 7,), "typestr": "<f4", "data": (ptr, False), "version": 2,
+                                                "strides": None}
+                aos_cache[(ptr, cap)] = torch.as_tensor(_V(), device=f"cuda:{local}")
+            return aos_cache[(ptr, cap)]
+
+        e2e_step()  # warm-up
+        a_in[:] = parts[c0:c1]
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            eng.upload(a_in, prm["id_count"])  # same-size re-upload: device buffers (and IPC mappings) stay put
-            stepper.reset()
-            stepper.step(P, TS, 1)
-            eng.download_into(a_out)
+            e2e_step()
+            a_in, a_out = a_out, a_in  # src/lib.rs:167 swap
         barrier()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
         tt = torch.tensor([e2e_s], device=f"cuda:{local}")
@@ -494,7 +597,10 @@ def run_engine(args):
         e2e_s = float(tt.item())
         line["e2e"] = {"value": float(n) * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 28,
                        "d2h_bytes_per_step": n * 28, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                       "api": "per rank: p3d_upload + sharded step + p3d_download on pinned host arrays"}
+                       "api": f"per rank: p3d_upload_part (1/{world} of the array, pinned) + NCCL all-gather of the staging array + "
+                              "p3d_upload_commit + sharded step + p3d_download_part (1/G of the array); bytes are the job's "
+                              "totals over all ranks"}
+        reupload(parts)
 
     # ---------------- multi-GPU: where a step's time goes on every rank (diagnostic, outside the timed region) ----------------
     if world > 1 and fused:
@@ -537,9 +643,7 @@ def run_engine(args):
         other = "plummer" if args.cloud == "uniform" else "uniform"
         _, parts_o = workload(n, W, other)
         eng.set_option(_abi.OPT_TIMING, 0)
-        eng.upload(parts_o, prm["id_count"])  # same n: device buffers (and IPC mappings) stay put
-        if stepper:
-            stepper.reset()
+        reupload(parts_o)  # same n: device buffers (and IPC mappings) stay put
         o_steps = max(1, min(args.steps, 3))
         one_step()
         flush.zero_()
@@ -559,9 +663,7 @@ def run_engine(args):
         line["other_cloud"] = {"cloud": other, "what": f"same N, W and constants on a {'clustered (Plummer a=W/6, truncated to the box)' if other == 'plummer' else 'uniform'} cloud",
                                "steps": o_steps, "warmup": 1, "ms_per_step": o_ms, "steps_per_s": 1e3 / o_ms,
                                "value": float(n) * n / (o_ms * 1e-3), "unit": UNIT}
-        eng.upload(parts, prm["id_count"])
-        if stepper:
-            stepper.reset()
+        reupload(parts)
 
     # ---------------- "next" row: the cell-list path on the same workload ----------------
     # Reported as effective steps/s only: it evaluates ~30 candidates per particle instead of N, so it
@@ -637,11 +739,19 @@ def run_engine(args):
             "ms_per_step": r["step_s"] * 1e3, "steps_per_s": 1.0 / r["step_s"],
             "candidate_pairs_per_s": r["candidates_per_particle"] * n / r["step_s"],
         }
+        line["cpu_cores"] = r["cores"]
     if rank == 0:
         emit(line)
+    if world > 1:
+        dist.barrier()
+        eng.ipc_close()
+        dist.barrier()
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        sys.stderr.write(f"bench.py: PARITY FAILED: {json.dumps(parity)}\n")
+        sys.exit(1)
 
 
 def main():
@@ -657,6 +767,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity step (it is outside the timed region)")
     ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-reduce + all-gather instead of the fused P2P kernel")
     ap.add_argument("--no-cells", action="store_true", help="skip the cell-list (SURVEY §8f-1) section")
     ap.add_argument("--cloud", default="uniform", choices=["uniform", "plummer"],

@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define P3D_ABI_VERSION 1
+#define P3D_ABI_VERSION 2
 
 /* ---- error codes (the Rust shim turns non-zero into the panic the reference would raise) ---- */
 #define P3D_OK 0
@@ -61,6 +61,16 @@ int p3d_abi_version(void);
 /* Creates an engine on CUDA device `device`.  Not thread-safe: one caller at a time per handle
  * (mirrors `&mut self` at src/lib.rs:130). */
 int p3d_create(int device, p3d_engine **out);
+/* One handle that drives n_dev (1..8) devices of one node from the calling thread - the form the Rust shim uses
+ * (`Particles::update` has a single caller and a single thread, src/bin/main.rs:199).  No IPC, no
+ * NCCL, no second process: the devices reach each other's buffers by peer access, cross-device CUDA events are the
+ * two barriers of a step.  p3d_upload / p3d_update split the caller's array so that every device moves 1/n_dev of
+ * it over its own PCIe link and gathers the rest over NVLink; every device holds the whole state after each step.
+ * Every whole-state call works on the handle (p3d_update, p3d_upload, p3d_step, p3d_download, p3d_download_forces,
+ * p3d_download_render, p3d_diagnostics, p3d_sync, options, counters); the p3d_shard_*, p3d_ipc_*, p3d_set_stream,
+ * p3d_device_buffer and per-kernel timing calls return P3D_ERR_INVALID on it.  A device may be listed more than once
+ * (the members then share it; exercises the same code on a one-GPU box). */
+int p3d_create_multi(const int *devices, int n_dev, p3d_engine **out);
 void p3d_destroy(p3d_engine *eng);
 /* Message for the last non-zero return on this thread. */
 const char *p3d_last_error(void);
@@ -78,6 +88,9 @@ int p3d_upload(p3d_engine *eng, const p3d_particle *in, size_t n, uint32_t id_co
 int p3d_step(p3d_engine *eng, const p3d_params *prm, float ts, int n_steps);
 int p3d_download(p3d_engine *eng, p3d_particle *out, size_t n);
 int p3d_sync(p3d_engine *eng);
+/* Caller index -> slot of the resident layout (identity unless the pair kernel's type-grouped layout is active);
+ * slot / (n_slots / world) is the rank that integrates the particle.  For tests and the bench's parity sample. */
+int p3d_slot_of(p3d_engine *eng, uint32_t *out, size_t n);
 /* The resident state in the layout of the reference app's render storage buffer:
  * WGSL `struct Particles { world_size: f32, length: u32, particles: array<Particle> }` with 32-byte particles
  * (position vec3 @0, velocity vec3 @16, id u32 @28; src/bin/particles.wgsl:1-12).  Replaces the per-frame CPU
@@ -130,44 +143,56 @@ enum p3d_buffer {
     P3D_BUF_POS = 0,      /* float4 {x,y,z,id bits} per slot, current positions */
     P3D_BUF_POS_NEXT = 1, /* float4 per slot, written by integrate */
     P3D_BUF_VEL = 2,      /* float4 {vx,vy,vz,0} per slot */
-    P3D_BUF_FORCE = 3     /* float4 {fx,fy,fz,0} per slot */
+    P3D_BUF_FORCE = 3,    /* float4 {fx,fy,fz,0} per slot */
+    P3D_BUF_AOS = 4       /* staging array of the sharded upload: 7 words per caller index (p3d_particle), element
+                             count = world * ceil(n / world) particles; valid after p3d_upload_part */
 };
 /* Device pointer + element count (slots, >= n because type segments are padded). */
 int p3d_device_buffer(p3d_engine *eng, int which, void **dev_ptr, size_t *n_slots);
-/* Shard = the slot range this rank integrates and, for the force pass, its share of block rows.
- * world==1 restores single-GPU behaviour.  Call BEFORE p3d_upload: the slot layout is padded so that
- * all ranks own equally many slots.  While world > 1 the whole-step calls (p3d_update, p3d_step) return
- * P3D_ERR_INVALID: a step then needs the driver's collectives between the p3d_shard_* calls below. */
+/* Shard = the slot range this rank integrates and, for the force pass, its share of the work (block rows of the
+ * pair kernel, cell-sorted index range of the cell list, slot range of the reference-order kernel).
+ * world==1 restores single-GPU behaviour.  Call BEFORE p3d_upload: the slot layout is padded so that all ranks own
+ * equally many slots; changing `world` afterwards drops the resident state (upload again).  While world > 1 the
+ * whole-step calls (p3d_update, p3d_step) return P3D_ERR_INVALID: a step then needs the driver's collectives
+ * between the p3d_shard_* calls below. */
 int p3d_set_shard(p3d_engine *eng, int rank, int world);
 int p3d_shard_range(p3d_engine *eng, size_t *slot_begin, size_t *slot_end);
 /* One step split at the collectives a multi-GPU driver inserts:
- *   p3d_shard_force     -> partial forces (this rank's block rows) into P3D_BUF_FORCE
- *   [driver: sum-reduce P3D_BUF_FORCE across ranks when the PAIR kernel is used]
+ *   p3d_shard_force     -> PARTIAL forces into P3D_BUF_FORCE: every kernel zeroes the buffer and then adds / scatters
+ *                          its share, so a rank's own slots receive contributions computed on other ranks
+ *   [driver: sum-reduce P3D_BUF_FORCE across ranks - REQUIRED for P3D_FORCE_PAIR, P3D_FORCE_CELLS, P3D_OPT_FAITHFUL
+ *    and P3D_FORCE_AUTO; only P3D_FORCE_REFERENCE_ORDER without the faithful option writes complete forces for
+ *    exactly the rank's own slot range and may skip it]
  *   p3d_shard_integrate -> integrates [slot_begin,slot_end) into P3D_BUF_POS_NEXT / P3D_BUF_VEL
- *   [driver: all-gather P3D_BUF_POS_NEXT across ranks]
+ *   [driver: all-gather P3D_BUF_POS_NEXT (and P3D_BUF_VEL, if any rank is to download the whole state)]
  *   p3d_shard_commit    -> swaps POS/POS_NEXT */
 int p3d_shard_force(p3d_engine *eng, const p3d_params *prm);
 int p3d_shard_integrate(p3d_engine *eng, const p3d_params *prm, float ts);
 int p3d_shard_commit(p3d_engine *eng);
 
+/* Sharded host <-> device traffic for one-process-per-GPU drivers: every rank moves only ITS part of the caller's
+ * array over its own PCIe link.
+ *   p3d_upload_part   -> callers [i_begin, i_end) of n into the staging array (P3D_BUF_AOS); synchronous
+ *   [driver: all-gather P3D_BUF_AOS across ranks (equal parts of ceil(n / world) particles)]
+ *   p3d_upload_commit -> layout + pack from the staging array (what p3d_upload does after its copy)
+ *   p3d_download_part -> callers [i_begin, i_end) of the resident state (every rank holds the whole state after a
+ *                        fused step, or after the driver gathered positions and velocities) */
+int p3d_upload_part(p3d_engine *eng, const p3d_particle *part, size_t i_begin, size_t i_end, size_t n, uint32_t id_count);
+int p3d_upload_commit(p3d_engine *eng);
+int p3d_download_part(p3d_engine *eng, p3d_particle *out_part, size_t i_begin, size_t i_end);
+
 /* Fused variant of the step's second half over NVLink peer memory (one kernel = reduce-scatter of the
- * partial forces + integrate + all-gather of the new positions; no NCCL on the data path):
- *   p3d_ipc_export  -> three 64-byte CUDA IPC handles (force buffer, both position buffers) of this rank
+ * partial forces + integrate + all-gather of the new positions and velocities; no NCCL on the data path):
+ *   p3d_ipc_export  -> four 64-byte CUDA IPC handles (force buffer, both position buffers, velocities) of this rank
  *   [driver: all-gather the handles]
  *   p3d_ipc_import  -> opens every peer's buffers (world <= 8, same node, after p3d_upload on all ranks)
  *   per step: p3d_shard_force; [barrier]; p3d_shard_integrate_fused; [barrier]; p3d_shard_commit */
-int p3d_ipc_export(p3d_engine *eng, unsigned char *handles /* 3 * 64 bytes */);
-int p3d_ipc_import(p3d_engine *eng, int world, const unsigned char *all_handles /* world * 3 * 64 bytes */);
+#define P3D_IPC_HANDLES 4
+int p3d_ipc_export(p3d_engine *eng, unsigned char *handles /* P3D_IPC_HANDLES * 64 bytes */);
+int p3d_ipc_import(p3d_engine *eng, int world, const unsigned char *all_handles /* world * P3D_IPC_HANDLES * 64 bytes */);
 int p3d_ipc_close(p3d_engine *eng);
 int p3d_shard_integrate_fused(p3d_engine *eng, const p3d_params *prm, float ts);
 
-/* ---- FP32-pipe microbenchmarks: make the roofline denominator defensible ----
- * kind 0: dependent-chain-free scalar FFMA; 1: packed FFMA2; 2: the pair kernel's instruction mix
- * (17 FFMA2/FADD2 : 2 MUFU.RSQ : 6 FMNMX); 3: FFMA2 with the pair kernel's shuffle rate (12 SHFL per 68 FFMA2).
- * kinds 4..17 are instruction-mix and register-operand-bandwidth probes used in DESIGN.md §5 (out[0] = thread-bodies/s).
- * out[0] = FP32 lane-FMAs per second (an FFMA2 counts 2 per lane), out[1] = kernel ms,
- * out[2] = SM count, out[3] = max SM clock in MHz as reported by the driver. */
-int p3d_microbench(int device, int kind, int iters, double out[4]);
 /* Self-checking builds (-DP3D_BOUNDS_CHECK: every data-dependent slot / cell index in the kernels is compared
  * with its extent, violations are counted and the access skipped): number of violations since the library was
  * loaded.  A product build stores UINT64_MAX.  (No reference counterpart: Rust's slice indexing panics,

@@ -93,6 +93,15 @@ def lib():
         L.ora_integrate.restype = None
         L.ora_integrate.argtypes = [C.POINTER(_Params), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.ora_num_threads.restype = C.c_int
+        L.ora_update_indices.restype = C.c_int
+        L.ora_update_indices.argtypes = [C.POINTER(_Params), C.c_float, C.c_void_p, C.c_void_p, C.c_size_t,
+                                         C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Stats), C.c_int]
+        L.ora_scene_default_params.restype = None
+        L.ora_scene_default_params.argtypes = [C.POINTER(_Params), C.POINTER(C.c_float)]
+        L.ora_scene_uniform.restype = None
+        L.ora_scene_uniform.argtypes = [C.c_uint64, C.c_size_t, C.c_float, C.c_uint32, C.c_void_p]
+        L.ora_scene_plummer.restype = None
+        L.ora_scene_plummer.argtypes = [C.c_uint64, C.c_size_t, C.c_float, C.c_float, C.c_uint32, C.c_void_p]
         _lib = L
     return _lib
 
@@ -180,6 +189,43 @@ def update_sample(params: dict, ts: float, particles: np.ndarray, i_begin: int, 
     if rc:
         raise AssertionError(f"oracle rc={rc}")
     return out, st.asdict()
+
+
+def update_indices(params: dict, ts: float, particles: np.ndarray, indices, mode: int = IDEAL, nthreads: int = 0):
+    """Advance only particles `indices` of one step (hash table over all n); returns (out, stats), out[k] = particle indices[k]."""
+    inp = np.ascontiguousarray(particles)
+    idx = np.ascontiguousarray(indices, dtype=np.uint64)
+    out = np.empty(idx.shape[0], dtype=PARTICLE)
+    st = Stats()
+    prm, _keep = _mk_params(params)
+    rc = lib().ora_update_indices(C.byref(prm), ts, inp.ctypes.data, out.ctypes.data, inp.shape[0],
+                                  idx.ctypes.data, idx.shape[0], mode, C.byref(st), nthreads)
+    if rc:
+        raise AssertionError(f"oracle rc={rc}")
+    return out, st.asdict()
+
+
+def default_params_dict() -> dict:
+    """Default scene constants (src/bin/main.rs:123-148) as the dict the oracle entry points take."""
+    prm = _Params()
+    mat = (C.c_float * 25)()
+    lib().ora_scene_default_params(C.byref(prm), mat)
+    return dict(world_size=prm.world_size, coefficient=prm.coefficient, interaction_force=prm.interaction_force,
+                min_pull_ratio=prm.min_pull_ratio, particle_effect_radius=prm.particle_effect_radius,
+                id_count=int(prm.id_count), attraction_matrix=[float(x) for x in mat], walls=bool(prm.walls),
+                acceleration=tuple(float(x) for x in prm.accel))
+
+
+def scene_uniform(world_size: float, count: int, seed: int = 42, id_count: int = 5) -> np.ndarray:
+    out = np.zeros(count, dtype=PARTICLE)
+    lib().ora_scene_uniform(seed, count, world_size, id_count, out.ctypes.data)
+    return out
+
+
+def scene_plummer(world_size: float, count: int, scale_a: float, seed: int = 42, id_count: int = 5) -> np.ndarray:
+    out = np.zeros(count, dtype=PARTICLE)
+    lib().ora_scene_plummer(seed, count, world_size, scale_a, id_count, out.ctypes.data)
+    return out
 
 
 def bruteforce_forces(params: dict, particles: np.ndarray, nthreads: int = 0) -> np.ndarray:

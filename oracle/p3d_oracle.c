@@ -192,13 +192,13 @@ int ora_num_threads(void) {
 
 /* lib.rs:130-272 */
 static int ora_update_impl(const ora_params *prm, float ts, const ora_particle *in, ora_particle *out,
-                           size_t n, size_t i_begin, size_t i_end, int mode, int acc64, float *force_out,
-                           uint8_t *affected, ora_stats *stats, int nthreads);
+                           size_t n, size_t i_begin, size_t i_end, const size_t *idx, int mode, int acc64,
+                           float *force_out, uint8_t *affected, ora_stats *stats, int nthreads);
 
 int ora_update(const ora_params *prm, float ts, const ora_particle *in, ora_particle *out,
                size_t n, int mode, int acc64, float *force_out, uint8_t *affected,
                ora_stats *stats, int nthreads) {
-    return ora_update_impl(prm, ts, in, out, n, 0, n, mode, acc64, force_out, affected, stats, nthreads);
+    return ora_update_impl(prm, ts, in, out, n, 0, n, NULL, mode, acc64, force_out, affected, stats, nthreads);
 }
 
 /* Same step, but only particles [i_begin, i_end) are advanced (out, force_out, affected hold
@@ -208,7 +208,18 @@ int ora_update_sample(const ora_params *prm, float ts, const ora_particle *in, o
                       size_t n, size_t i_begin, size_t i_end, int mode, ora_stats *stats, int nthreads) {
     if (i_end > n) i_end = n;
     if (i_begin > i_end) i_begin = i_end;
-    return ora_update_impl(prm, ts, in, out, n, i_begin, i_end, mode, 0, NULL, NULL, stats, nthreads);
+    return ora_update_impl(prm, ts, in, out, n, i_begin, i_end, NULL, mode, 0, NULL, NULL, stats, nthreads);
+}
+
+/* Same step, but only the particles idx[0..n_idx) are advanced (out[k] = updated particle idx[k]); the hash
+ * table covers all n.  Lets a parity check at N = 1M sample particles from every type segment / every rank's
+ * slot range instead of one contiguous index range. */
+int ora_update_indices(const ora_params *prm, float ts, const ora_particle *in, ora_particle *out, size_t n,
+                       const size_t *idx, size_t n_idx, int mode, ora_stats *stats, int nthreads) {
+    if (n_idx && !idx) return 4;
+    for (size_t k = 0; k < n_idx; ++k)
+        if (idx[k] >= n) return 4;
+    return ora_update_impl(prm, ts, in, out, n, 0, n_idx, idx, mode, 0, NULL, NULL, stats, nthreads);
 }
 
 static double now_s(void) {
@@ -220,8 +231,8 @@ static double now_s(void) {
 }
 
 static int ora_update_impl(const ora_params *prm, float ts, const ora_particle *in, ora_particle *out,
-                           size_t n, size_t i_begin, size_t i_end, int mode, int acc64, float *force_out,
-                           uint8_t *affected, ora_stats *stats, int nthreads) {
+                           size_t n, size_t i_begin, size_t i_end, const size_t *idx, int mode, int acc64,
+                           float *force_out, uint8_t *affected, ora_stats *stats, int nthreads) {
     const double t_start = now_s();
     const float W = prm->world_size, r = prm->particle_effect_radius, m = prm->min_pull_ratio;
     const uint32_t T = prm->id_count;
@@ -264,7 +275,8 @@ static int ora_update_impl(const ora_params *prm, float ts, const ora_particle *
 
 #pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads) \
     reduction(+ : s_cand, s_in, s_nz, s_dupq, s_aff)
-    for (size_t i = i_begin; i < i_end; ++i) {
+    for (size_t k = i_begin; k < i_end; ++k) {
+        const size_t i = idx ? idx[k] : k;
         const ora_particle p = in[i]; /* past_particles[i], :171-174 */
         float ax = 0.0f, ay = 0.0f, az = 0.0f;
         double dax = 0.0, day = 0.0, daz = 0.0;
@@ -327,7 +339,7 @@ static int ora_update_impl(const ora_params *prm, float ts, const ora_particle *
                 }
         if (acc64) { ax = (float)dax; ay = (float)day; az = (float)daz; }
         const float F[3] = {ax, ay, az};
-        const size_t o = i - i_begin;
+        const size_t o = k - i_begin;
         if (force_out) { force_out[3 * o] = ax; force_out[3 * o + 1] = ay; force_out[3 * o + 2] = az; }
         if (affected) affected[o] = (uint8_t)hit_dup;
         s_aff += (uint64_t)hit_dup;
@@ -389,4 +401,81 @@ int ora_bruteforce_forces(const ora_params *prm, const ora_particle *in, size_t 
         force_out[3 * i] = ax; force_out[3 * i + 1] = ay; force_out[3 * i + 2] = az;
     }
     return 0;
+}
+
+
+/* ---- seeded scenes for the bench's reference arm -------------------------------------------------
+ * The reference's generator (src/bin/main.rs:60-87) is unseeded, so the bench uses its own
+ * counter-based stream (splitmix64, seed 42).  The product has the same generator
+ * (p3d_scene_uniform / p3d_scene_plummer); it is restated here so that the reference arm builds its
+ * inputs without loading the product library.  tests/test_oracle_scene.py requires byte equality. */
+static uint64_t sm64_next(uint64_t *state) {
+    uint64_t z = (*state += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+static float sm64_unit_f32(uint64_t *state) { return (float)(sm64_next(state) >> 40) * (1.0f / 16777216.0f); }
+static double sm64_unit_f64(uint64_t *state) {
+    return (double)(sm64_next(state) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+/* default scene constants, src/bin/main.rs:123-148; matrix25 receives the 5x5 matrix of :133-139 */
+void ora_scene_default_params(ora_params *prm, float matrix25[25]) {
+    static const float rows[5][5] = {{0.5f, 1.0f, -0.5f, 0.0f, -1.0f},
+                                     {1.0f, 1.0f, 1.0f, 0.0f, -1.0f},
+                                     {0.0f, 0.0f, 0.5f, 1.5f, -1.0f},
+                                     {0.0f, 0.0f, 0.0f, 0.0f, -1.0f},
+                                     {1.0f, 1.0f, 1.0f, 1.0f, 0.5f}};
+    for (int i = 0; i < 5; ++i)
+        for (int j = 0; j < 5; ++j) matrix25[5 * i + j] = rows[i][j];
+    prm->world_size = 10.0f;
+    prm->coefficient = 0.97f;
+    prm->interaction_force = 1.0f;
+    prm->min_pull_ratio = 0.3f;
+    prm->particle_effect_radius = 2.0f;
+    prm->accel[0] = prm->accel[1] = prm->accel[2] = 0.0f;
+    prm->walls = 0;
+    prm->id_count = 5;
+    prm->attraction_matrix = matrix25;
+}
+
+/* uniform box [-W/2, W/2)^3, v = 0, id uniform in 0..id_count (distribution of main.rs:60-87) */
+void ora_scene_uniform(uint64_t seed, size_t n, float world_size, uint32_t id_count, ora_particle *out) {
+    uint64_t st = seed;
+    const float half = world_size * 0.5f;
+    for (size_t i = 0; i < n; ++i) {
+        ora_particle *p = &out[i];
+        p->px = -half + world_size * sm64_unit_f32(&st);
+        p->py = -half + world_size * sm64_unit_f32(&st);
+        p->pz = -half + world_size * sm64_unit_f32(&st);
+        p->vx = 0.0f; p->vy = 0.0f; p->vz = 0.0f;
+        p->id = id_count ? (uint32_t)(sm64_next(&st) % id_count) : 0u;
+    }
+}
+
+/* Plummer-like cloud (BASELINE.json config 3): radius from the inverted Plummer mass profile with scale a,
+ * isotropic direction, samples outside the box rejected. */
+void ora_scene_plummer(uint64_t seed, size_t n, float world_size, float scale_a, uint32_t id_count,
+                       ora_particle *out) {
+    uint64_t st = seed;
+    const double half = 0.5 * (double)world_size;
+    for (size_t i = 0; i < n; ++i) {
+        double x, y, z;
+        do {
+            double u = sm64_unit_f64(&st);
+            if (u < 1e-12) u = 1e-12;
+            const double rad = (double)scale_a / sqrt(pow(u, -2.0 / 3.0) - 1.0);
+            const double cz = 2.0 * sm64_unit_f64(&st) - 1.0;
+            const double phi = 6.283185307179586476925286766559 * sm64_unit_f64(&st);
+            const double sz = sqrt(1.0 - cz * cz);
+            x = rad * sz * cos(phi);
+            y = rad * sz * sin(phi);
+            z = rad * cz;
+        } while (!(fabs(x) < half && fabs(y) < half && fabs(z) < half));
+        ora_particle *p = &out[i];
+        p->px = (float)x; p->py = (float)y; p->pz = (float)z;
+        p->vx = 0.0f; p->vy = 0.0f; p->vz = 0.0f;
+        p->id = id_count ? (uint32_t)(sm64_next(&st) % id_count) : 0u;
+    }
 }

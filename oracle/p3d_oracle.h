@@ -86,6 +86,11 @@ int ora_update(const ora_params *prm, float ts, const ora_particle *in, ora_part
 int ora_update_sample(const ora_params *prm, float ts, const ora_particle *in, ora_particle *out,
                       size_t n, size_t i_begin, size_t i_end, int mode, ora_stats *stats, int nthreads);
 
+/* Advance only the particles idx[0..n_idx) (out[k] = updated particle idx[k]); the hash table covers all n.
+ * Returns 4 for an index >= n. */
+int ora_update_indices(const ora_params *prm, float ts, const ora_particle *in, ora_particle *out, size_t n,
+                       const size_t *idx, size_t n_idx, int mode, ora_stats *stats, int nthreads);
+
 /* Independent check: O(N^2 * 27) brute force over all particles and all 27 image offsets in
  * double precision, same cutoff and force law, each (j,image) counted once.  force_out n*3 doubles. */
 int ora_bruteforce_forces(const ora_params *prm, const ora_particle *in, size_t n,
@@ -96,6 +101,13 @@ void ora_integrate(const ora_params *prm, float ts, const ora_particle *in, cons
                    ora_particle *out, size_t n);
 
 int ora_num_threads(void);
+
+/* Seeded scenes for the bench's reference arm (same streams as the product's p3d_scene_*; byte equality is a
+ * CPU test): default constants of src/bin/main.rs:123-148, uniform cloud (main.rs:60-87), Plummer cloud. */
+void ora_scene_default_params(ora_params *prm, float matrix25[25]);
+void ora_scene_uniform(uint64_t seed, size_t n, float world_size, uint32_t id_count, ora_particle *out);
+void ora_scene_plummer(uint64_t seed, size_t n, float world_size, float scale_a, uint32_t id_count,
+                       ora_particle *out);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_struct_layout():
     lib = _abi.load()
-    assert lib.p3d_abi_version() == 1
+    assert lib.p3d_abi_version() == 2
     assert _abi.PARTICLE.itemsize == 28  # src/lib.rs:12-17: 2 x Vector3<f32> + u32
     assert [_abi.PARTICLE.fields[k][1] for k in ("px", "py", "pz", "vx", "vy", "vz", "id")] == [0, 4, 8, 12, 16, 20, 24]
     assert C.sizeof(_abi.Params) == 48 and _abi.Params.attraction_matrix.offset == 40
@@ -91,8 +91,21 @@ def test_no_cpu_fallback_without_device():
     sim = p3.default_scene(n=4)
     with pytest.raises(p3.P3DError):
         sim.update(1 / 60)
-    out = (C.c_double * 4)()
-    assert _abi.load().p3d_microbench(0, 1, 10, out) == _abi.ERR_NO_DEVICE
+    from tools import microbench
+
+    assert microbench.run(0, 1, 10)[0] == _abi.ERR_NO_DEVICE
+    with pytest.raises(p3.P3DError) as ei:
+        p3.Engine([0, 0])  # the multi-device handle fails the same way
+    assert ei.value.code == _abi.ERR_NO_DEVICE
+
+
+def test_microbench_is_not_in_the_product_library():
+    """Measurement infrastructure lives in its own library (include/p3d_microbench.h), not in libp3d.so."""
+    import subprocess
+
+    syms = subprocess.run(["nm", "-D", "--defined-only", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "p3d_microbench" not in syms
+    assert "p3d_update" in syms and "p3d_create_multi" in syms
 
 
 def test_product_does_not_reference_the_oracle():

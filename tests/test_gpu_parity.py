@@ -519,17 +519,71 @@ def test_graph_replay_matches_ordinary_launches(default_params, kernel):
         assert outs[0].tobytes() == outs[1].tobytes()
 
 
+# ---------------------------------------------------------------- full-size configs against the ORACLE
+def _sample_vs_oracle(prm, parts, out, idx, W, what, tol=1e-5):
+    """pos / vel of the sampled particles after one step against the CPU oracle (ideal mode), helpers.py metric."""
+    ref, _ = O.update_indices(prm, TS, parts, idx, mode=O.IDEAL)
+    assert np.array_equal(out["id"], parts["id"]), "ids / index order changed"
+    dv, dp = parity_errors(out[idx], ref, W)
+    assert dv.max() <= tol and dp.max() <= tol, f"{what}: dv {dv.max():.3e} dp {dp.max():.3e} > {tol}"
+    return dv.max(), dp.max()
+
+
+@pytest.mark.parametrize("kernel", [_abi.FORCE_PAIR, _abi.FORCE_CELLS], ids=["pair", "cells"])
+def test_config4_1m_default_asymmetric_matrix_vs_oracle(default_params, kernel):
+    """BASELINE config 4 at full size through p3d_update with the DEFAULT asymmetric matrix (main.rs:133-139; the
+    aij / aji orientation of the R = 8 pair kernel, indexing src/lib.rs:225-228): positions and velocities of
+    20,000 particles strided over all five type segments (4,000 per type, spread over each segment's whole slot
+    range) against the oracle."""
+    n, W = 1048576, 101.6
+    prm = dict(default_params, world_size=W)
+    parts = p3.generate_particles(W, n, seed=42)
+    eng = p3.Engine(0)
+    eng.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+    eng.set_option(_abi.OPT_BLOCK_SIZE, 256)
+    out = eng.update(p3.Engine.make_params(**prm), TS, parts)
+    slot = eng.slot_of()
+    eng.close()
+    idx = []
+    for t in range(5):
+        members = np.flatnonzero(parts["id"] == t)
+        members = members[np.argsort(slot[members], kind="stable")]  # ascending slot: stride covers the segment
+        idx.append(members[:: max(1, len(members) // 4000)][:4000])
+    idx = np.concatenate(idx)
+    assert len(idx) >= 16000 and len(np.unique(parts["id"][idx])) == 5
+    _sample_vs_oracle(prm, parts, out, idx, W, f"config 4, kernel {kernel}")
+
+
+@pytest.mark.parametrize("kernel", [_abi.FORCE_PAIR, _abi.FORCE_CELLS], ids=["pair", "cells"])
+def test_config3_262k_plummer_one_step_vs_oracle(default_params, kernel):
+    """BASELINE config 3 at full size, one step against the ORACLE (not GPU vs GPU): the 8,192 particles closest to
+    the centre of the Plummer cloud (the dense core: hundreds of in-range neighbours each) plus 8,192 drawn at random."""
+    n, W = 262144, 64.0
+    prm = dict(default_params, world_size=W)
+    parts = p3.generate_plummer(W, n, W / 6, seed=42)
+    eng = p3.Engine(0)
+    eng.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+    out = eng.update(p3.Engine.make_params(**prm), TS, parts)
+    eng.close()
+    r2 = parts["px"].astype(np.float64) ** 2 + parts["py"].astype(np.float64) ** 2 + parts["pz"].astype(np.float64) ** 2
+    core = np.argsort(r2)[:8192]
+    rest = np.setdiff1d(np.arange(n), core)
+    idx = np.concatenate([core, np.random.default_rng(3).choice(rest, 8192, replace=False)])
+    _sample_vs_oracle(prm, parts, out, idx, W, f"config 3, kernel {kernel}")
+
+
 # ---------------------------------------------------------------- roofline denominator
 def test_fp32_microbenchmark_confirms_the_roofline_denominator():
     """The FP32 roofline uses 148 SMs x 128 lanes x 2 flop x clock; the packed-FFMA2 microbenchmark must
     reach it (and must not exceed it: FFMA2 halves issue slots, it does not double throughput)."""
-    import ctypes as C
+    from tools import microbench
 
-    out = (C.c_double * 4)()
-    assert _abi.load().p3d_microbench(0, 1, 2000, out) == 0
+    rc, out = microbench.run(0, 1, 2000)
+    assert rc == 0
     peak = out[2] * 128 * out[3] * 1e6  # lane-FMA/s at the maximum SM clock
     packed = out[0] / peak
-    assert _abi.load().p3d_microbench(0, 0, 2000, out) == 0  # scalar FFMA: same datapath, a bit lower
+    rc, out = microbench.run(0, 0, 2000)  # scalar FFMA: same datapath, a bit lower
+    assert rc == 0
     scalar = out[0] / peak
     assert packed <= 1.02 and scalar <= 1.02, (packed, scalar)  # exceeding the peak would be a counting error
     if packed < 0.90 or scalar < 0.80:

@@ -15,7 +15,7 @@ import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.join(ROOT, "3d-particle-simulation-_b200")); sys.path.insert(0, ROOT)
 import particle_3d as p3
 from particle_3d import _abi
-from particle_3d.sharded import ShardedStepper, engine_tensors, exchange_peer_handles
+from particle_3d.sharded import ShardedStepper, engine_tensors, exchange_peer_handles, sharded_upload, part_range
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -40,6 +40,16 @@ st = ShardedStepper(eng, dist, rank, world, lambda: engine_tensors(eng, local), 
 st.step(P, 1/60, steps)
 torch.cuda.synchronize()
 np.save(os.path.join(OUT, f"fused_{rank}.npy"), eng.download())
+# sharded host traffic: every rank uploads 1/world of the array, NCCL all-gathers the staging array, every rank
+# reads its own part of the result back (same device buffers: the IPC mappings stay valid)
+sharded_upload(eng, dist, rank, world, local, parts, 5)
+st.reset()
+st.step(P, 1/60, steps)
+torch.cuda.synchronize()
+c0, c1 = part_range(n, rank, world)
+mine = np.empty(c1 - c0, dtype=_abi.PARTICLE)
+eng.download_part_into(mine, c0)
+np.save(os.path.join(OUT, f"part_{rank}.npy"), mine)
 dist.barrier(); eng.ipc_close(); dist.barrier(); dist.destroy_process_group()
 '''
 
@@ -68,15 +78,18 @@ def test_two_gpu_sharded_step_matches_single_gpu_and_oracle(tmp_path, default_pa
         ref = O.update(prm, 1 / 60, ref, mode=O.IDEAL)["out"]
     for prefix in ("shard", "fused"):
         _check([np.load(tmp_path / f"{prefix}_{r}.npy") for r in range(world)], ref, W, prefix)
+    # the parts the ranks read back, concatenated, are the whole updated array in the caller's order
+    whole = np.concatenate([np.load(tmp_path / f"part_{r}.npy") for r in range(world)])
+    assert whole.shape == ref.shape
+    _check([whole], ref, W, "sharded upload + part download")
 
 
 def _check(outs, ref, W, what):
     from helpers import parity_errors
-    # after the final all-gather every rank holds every position; velocities only for its own shard,
-    # so compare positions on all ranks and velocities where some rank owns the slot
-    best = None
-    for got in outs:
+    # both variants gather positions AND velocities: every rank holds the whole state after a step
+    for r, got in enumerate(outs):
+        assert np.array_equal(got["id"], ref["id"]), what
         dv, dp = parity_errors(got, ref, W)
-        assert dp.max() < 5e-5, what
-        best = dv if best is None else np.minimum(best, dv)
-    assert best.max() < 5e-5, what  # every particle's velocity is right on its owner rank
+        assert dp.max() < 5e-5 and dv.max() < 5e-5, (what, r, dv.max(), dp.max())
+    for got in outs[1:]:
+        assert got.tobytes() == outs[0].tobytes(), f"{what}: the ranks' copies of the state differ"

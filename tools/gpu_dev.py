@@ -13,6 +13,7 @@ sys.path.insert(0, ROOT)
 import particle_3d as p3
 from particle_3d import _abi
 from oracle import oracle as O
+from tools import microbench as _mb
 
 
 def parity(n, W, kernel, steps=1, seed=42, plummer=False, block=0, **over):
@@ -90,7 +91,7 @@ def timing(n, W, kernel, steps=3, plummer=False, block=0, tune=0):
 
 
 def micro():
-    L = _abi.load()
+    L = _mb.load()
     for kind, name in ((0, "FFMA"), (1, "FFMA2"), (2, "pair-mix"), (3, "FFMA2+SHFL")):
         out = (C.c_double * 4)()
         rc = L.p3d_microbench(0, kind, 2000, out)
@@ -99,7 +100,7 @@ def micro():
 
 
 def micro2():
-    L = _abi.load()
+    L = _mb.load()
     names = {4: "6 FMNMX", 5: "2 MUFU.RSQ", 6: "3 SHFL", 7: "17 FFMA2 + 6 FMNMX", 8: "17 FFMA2 + 2 MUFU",
              9: "34 FFMA + 6 FMNMX + 2 MUFU", 10: "17 FFMA2 + 6 FMNMX + 2 MUFU", 11: "17 FFMA2 + 6 FMNMX + 2 MUFU + 3 SHFL",
              12: "17 FFMA2"}
@@ -112,7 +113,7 @@ def micro2():
 
 
 def micro3():
-    L = _abi.load()
+    L = _mb.load()
     names = {13: "8 FFMA2 d=a*b+d (3 distinct pairs)", 14: "8 FFMA2 d=a*a+d (2 distinct)", 15: "8 FFMA2 d=a*s+d (pair, scalar, pair)",
              16: "8 FFMA2 d=a*b+d, b shared by consecutive instrs", 17: "12 FFMA2 + 12 FFMA (disjoint)"}
     for kind in sorted(names):
@@ -123,7 +124,7 @@ def micro3():
 
 
 def micro4():
-    L = _abi.load()
+    L = _mb.load()
     names = {0: "F2 stream only (17 F2)", 1: "+MUFU", 2: "+FMNMX", 3: "+MUFU +FMNMX (= kernel body)", 4: "F2 only, no j-side (13 F2)",
              7: "kernel body, no j-side", 8: "F2 only, no i-side (14 F2 + 1 FADD2)", 11: "kernel body, no i-side", 12: "F2 only, no accumulation (11 F2)",
              16: "F2 only, i-positions as pairs", 19: "kernel body, i-positions as pairs", 32: "F2 only, no FADD2 (14 F2)", 35: "kernel body, no FADD2"}
@@ -137,7 +138,7 @@ def micro4():
 if __name__ == "__main__":
     what = sys.argv[1:] or ["parity", "timing", "micro"]
     if "micro5" in what:
-        L = _abi.load()
+        L = _mb.load()
         for kind, name in ((90, "two-phase G=2, F2 only (16 F2)"), (91, "two-phase G=4, F2 only"), (92, "two-phase G=8, F2 only"),
                            (93, "two-phase G=2, full body"), (94, "two-phase G=4, full body"), (95, "two-phase G=8, full body")):
             out = (C.c_double * 4)()
