@@ -17,7 +17,6 @@
 #include "p3d_kernels_pair.cuh"
 #include "p3d_kernels_cells.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
 
 static_assert(sizeof(p3d_particle) == 28, "boundary struct must be 28 bytes (src/lib.rs:12-17)");
 static_assert(sizeof(AosParticle) == 28, "device view of the boundary struct");
@@ -47,7 +46,7 @@ int fail(int code, const char *fmt, ...) {
 constexpr int kMaxTimedSteps = 512;
 constexpr int kEv = 5;  // events per timed step
 constexpr int kRefTile = 128;       // threads per CTA of the reference-order kernel
-constexpr int kOutOfBoxCellsMin = 32768;  // all-pairs path, out-of-box input, single-step call: cell list from this n
+constexpr int kOutOfBoxCellsMin = 32768;  // all-pairs path, out-of-box input: gated cell list from this n, exact kernel below
 constexpr int kPinWords = 128;     // pinned scratch words per engine (>= P3D_MAX_TYPES + 2)
 constexpr int kCellsAutoMin = 192;  // P3D_FORCE_AUTO uses the cell list from this n (its ~12 launches cost ~35 us),
                                     // the single-launch reference-order kernel below
@@ -101,9 +100,8 @@ struct p3d_engine {
     DevBuf<int> seg_start, seg_end, cnt;
     DevBuf<int2> cta_cnt, cta_off;
     // cell-list path
-    DevBuf<uint32_t> ckeys[2], cvals[2], cell_off;
+    DevBuf<uint32_t> ckeys[2], cvals[2], crank, cell_cnt, cell_off, scan_tiles;
     DevBuf<float4> cpos;
-    DevBuf<unsigned char> cub_tmp;
     DevBuf<float> aos, fout, sx, sy, sz;
     DevBuf<float4> render;
     DevBuf<float> matrix;
@@ -125,7 +123,6 @@ struct p3d_engine {
     int opt_block_sort = 1;
     int opt_faithful = 0;    // K5: add the reference's bucket double-visit contributions
     int opt_graph = 1;       // replay device-resident multi-step runs through a CUDA graph (two steps per graph)
-    int force_override = -1; // >= 0: force kernel for the steps of the current call (see run_steps)
 
     // CUDA graph of two consecutive steps (returns cur/parity to their starting values)
     cudaGraphExec_t graph_exec = nullptr;
@@ -385,16 +382,14 @@ int resolve_force_kernel_for(const p3d_engine *e, size_t n) {
     return e->opt_force;
 }
 int resolve_force_kernel(const p3d_engine *e) {
-    return e->force_override >= 0 ? e->force_override : resolve_force_kernel_for(e, e->n);
+    return resolve_force_kernel_for(e, e->n);
 }
 
 size_t ref_smem(int tile, int T) { return (size_t)tile * sizeof(float4) + (size_t)T * T * sizeof(float); }
 
-// Sorts the slots by grid cell (cells of edge W/nc >= reach; at most ~8 cells per particle so sparse
-// scenes stay cheap).  g.nc < 3 on return: the box is narrower than three cells, no cell list was built.
-int build_cells(p3d_engine *e, const DevParams &P, const float4 *pos, int *flag_to_clear, CellGrid &g) {
-    cudaStream_t st = e->stream;
-    const int ns = e->n_slots;
+// Grid for the cell list: cells of edge W/nc >= reach, at most ~8 cells per particle so sparse scenes stay cheap.
+// g.nc < 3: the box is narrower than three cells, no cell list can be built.
+void cell_grid_for(const p3d_engine *e, const DevParams &P, CellGrid &g) {
     const float reach = P.reach * 1.001f + 1.0e-4f;
     long long nc = (long long)std::floor((double)P.W / (double)reach);
     const long long cap = (long long)std::cbrt(8.0 * (double)std::max<size_t>(e->n, 64)) + 1;
@@ -402,33 +397,46 @@ int build_cells(p3d_engine *e, const DevParams &P, const float4 *pos, int *flag_
     g.nc = (int)std::max<long long>(nc, 0);
     g.inv_cs = (float)((double)nc / (double)P.W);
     g.half = P.half;
+}
+
+// Sorts the slots by grid cell with a counting sort (k_cell_count, three scan kernels, k_cell_scatter,
+// k_cell_order: the GPU analogue of src/lib.rs:135-164).  gate/gate_value: see P3D_GATED.
+int build_cells(p3d_engine *e, const DevParams &P, const float4 *pos, int *flag_to_clear, CellGrid &g,
+                const int *gate = nullptr, int gate_value = 0) {
+    cudaStream_t st = e->stream;
+    const int ns = e->n_slots;
+    cell_grid_for(e, P, g);
+    const long long nc = g.nc;
     if (nc < 3) {
-        CU(cudaMemsetAsync(flag_to_clear, 0, sizeof(int), st));
+        if (flag_to_clear) CU(cudaMemsetAsync(flag_to_clear, 0, sizeof(int), st));
         return P3D_OK;
     }
     const size_t ncell = (size_t)(nc * nc * nc);
+    const int L = (int)ncell + 1;                       // + the ghost bin
+    const int tiles = (L + kScanTile - 1) / kScanTile;
     int rc;
     for (int k = 0; k < 2; ++k) {
         if ((rc = e->ckeys[k].ensure((size_t)ns))) return rc;
         if ((rc = e->cvals[k].ensure((size_t)ns))) return rc;
     }
+    if ((rc = e->crank.ensure((size_t)ns))) return rc;
     if ((rc = e->cpos.ensure((size_t)ns))) return rc;
+    if ((rc = e->cell_cnt.ensure(ncell + 2))) return rc;
     if ((rc = e->cell_off.ensure(ncell + 2))) return rc;
+    if ((rc = e->scan_tiles.ensure((size_t)tiles + 1))) return rc;
 #ifdef P3D_BOUNDS_CHECK
     k_debug_publish<<<1, 1, 0, st>>>(0xFFFFFFFFu, (unsigned int)ncell);
 #endif
-    int end_bit = 1;
-    while ((1ull << end_bit) <= ncell) ++end_bit;
-    size_t tmp_bytes = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, e->ckeys[0].p, e->ckeys[1].p, e->cvals[0].p, e->cvals[1].p,
-                                       ns, 0, end_bit, st));
-    if ((rc = e->cub_tmp.ensure(tmp_bytes))) return rc;
-    k_cell_keys<<<(ns + 255) / 256, 256, 0, st>>>(pos, ns, g, e->ckeys[0].p, e->cvals[0].p, flag_to_clear);
-    CU(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp_bytes, e->ckeys[0].p, e->ckeys[1].p, e->cvals[0].p,
-                                       e->cvals[1].p, ns, 0, end_bit, st));
-    k_cell_gather<<<(ns + 255) / 256, 256, 0, st>>>(pos, ns, e->ckeys[1].p, e->cvals[1].p, e->cpos.p, e->cell_off.p,
-                                                   (uint32_t)ncell);
-    e->counters[0] += 3;
+    const unsigned grid = (unsigned)((ns + 255) / 256);
+    CU(cudaMemsetAsync(e->cell_cnt.p, 0, (size_t)L * sizeof(uint32_t), st));
+    k_cell_count<<<grid, 256, 0, st>>>(pos, ns, g, e->ckeys[0].p, e->crank.p, e->cell_cnt.p, flag_to_clear, gate, gate_value);
+    k_scan_tile_sums<<<tiles, kScanThreads, 0, st>>>(e->cell_cnt.p, L, e->scan_tiles.p, gate, gate_value);
+    k_scan_top<<<1, kScanThreads, 0, st>>>(e->scan_tiles.p, tiles, gate, gate_value);
+    k_scan_apply<<<tiles, kScanThreads, 0, st>>>(e->cell_cnt.p, L, e->scan_tiles.p, e->cell_off.p, gate, gate_value);
+    k_cell_scatter<<<grid, 256, 0, st>>>(ns, e->ckeys[0].p, e->crank.p, e->cell_off.p, e->cvals[0].p, gate, gate_value);
+    k_cell_order<<<grid, 256, 0, st>>>(pos, ns, e->ckeys[0].p, e->crank.p, e->cell_off.p, e->cvals[0].p, (uint32_t)ncell,
+                                       e->ckeys[1].p, e->cvals[1].p, e->cpos.p, gate, gate_value);
+    e->counters[0] += 6;
     CU(cudaGetLastError());
     return P3D_OK;
 }
@@ -507,8 +515,9 @@ int launch_force(p3d_engine *e, const DevParams &P) {
                 // in-box positions (flag clear): the image follows from the neighbour cell ...
                 if (P.rcut) k_force_cells<true, false><<<cg, kCellThreads, sm, st>>>(P3D_CELL_ARGS);
                 else        k_force_cells<false, false><<<cg, kCellThreads, sm, st>>>(P3D_CELL_ARGS);
-                // ... some particle outside the box (flag set): nearest of the reference's three images per axis
-                k_force_cells<true, true><<<cg, kCellThreads, sm, st>>>(P3D_CELL_ARGS);
+                // ... some particle outside the box (flag set): nearest of the reference's three images per axis.  Rare,
+                // so it gets a small grid (it strides over the particles) and costs nothing when it does not run.
+                k_force_cells<true, true><<<std::min(cg, (unsigned)(8 * e->sm_count)), kCellThreads, sm, st>>>(P3D_CELL_ARGS);
 #undef P3D_CELL_ARGS
                 e->counters[0] += 2;
                 e->counters[1]++;
@@ -608,14 +617,33 @@ int launch_force(p3d_engine *e, const DevParams &P) {
         e->counters[1] += 2;
     }
     else if (e->step_ev) CU(cudaEventRecord(e->step_ev[2], st));
-    // out-of-box inputs (flag set): the reference-order kernel takes the whole step instead
+    // Out-of-box input (flag set: the pair kernels above returned at once).  The same images are evaluated by the
+    // cell list's general variant, O(N x neighbours), queued BEHIND the flag on the device (no host round trip, so a
+    // device-resident multi-step run is covered too); small systems and boxes narrower than three cells take the
+    // exact all-pairs kernel instead.
     {
-        const int per = ((M + e->world - 1) / e->world) * B;
-        const int i0 = std::min(ns, e->rank * per), i1 = std::min(ns, i0 + per);
-        if (i1 > i0) {
-            k_force_ref<kRefTile><<<(i1 - i0 + kRefTile - 1) / kRefTile, kRefTile, ref_smem(kRefTile, P.T), st>>>(
-                pos, ns, i0, i1, e->frc.p, P, e->matrix.p, flag_cur, 1);
-            e->counters[0]++;
+        CellGrid g;
+        cell_grid_for(e, P, g);
+        if (e->n >= (size_t)kOutOfBoxCellsMin && g.nc >= 3) {
+            int rc;
+            if ((rc = build_cells(e, P, pos, nullptr, g, flag_cur, 1))) return rc;
+            const int per = (ns + e->world - 1) / e->world;
+            const int i0 = std::min(ns, e->rank * per), i1 = std::min(ns, i0 + per);
+            if (i1 > i0) {
+                k_force_cells<true, true><<<std::min((unsigned)((i1 - i0 + kCellThreads - 1) / kCellThreads),
+                                                     (unsigned)(8 * e->sm_count)), kCellThreads,
+                                            (size_t)P.T * P.T * sizeof(float), st>>>(
+                    e->cpos.p, e->ckeys[1].p, e->cvals[1].p, e->cell_off.p, ns, i0, i1, g, e->frc.p, P, e->matrix.p, flag_cur);
+                e->counters[0]++;
+            }
+        } else {
+            const int per = ((M + e->world - 1) / e->world) * B;
+            const int i0 = std::min(ns, e->rank * per), i1 = std::min(ns, i0 + per);
+            if (i1 > i0) {
+                k_force_ref<kRefTile><<<(i1 - i0 + kRefTile - 1) / kRefTile, kRefTile, ref_smem(kRefTile, P.T), st>>>(
+                    pos, ns, i0, i1, e->frc.p, P, e->matrix.p, flag_cur, 1);
+                e->counters[0]++;
+            }
         }
     }
     CU(cudaGetLastError());
@@ -742,19 +770,6 @@ int run_steps(p3d_engine *e, const p3d_params *prm, const DevParams &P, float ts
     int rc;
     if ((rc = upload_matrix(e, prm))) return rc;
     if ((rc = check_box_now(e, P))) return rc;  // world_size may have changed since the last call
-    // All-pairs kernel with a particle outside the box: on the device the exact O(27 N^2) reference-order kernel
-    // takes such a step over, which is minutes at N = 1M.  A single-step call (p3d_update) can afford to look at
-    // the flag: the cell list's general variant evaluates the same images in O(N), whatever the layout.
-    struct OverrideGuard {
-        p3d_engine *e;
-        ~OverrideGuard() { e->force_override = -1; }
-    } guard{e};
-    if (n_steps == 1 && e->world == 1 && e->n >= (size_t)kOutOfBoxCellsMin && resolve_force_kernel(e) == P3D_FORCE_PAIR) {
-        int outside = 0;
-        CU(cudaMemcpyAsync(&outside, e->flags.p + e->parity, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
-        if (outside) e->force_override = P3D_FORCE_CELLS;
-    }
     e->timed_steps = 0;
     if (e->opt_timing && (rc = ensure_events(e, n_steps))) return rc;
     int s = 0;
@@ -883,7 +898,7 @@ void p3d_destroy(p3d_engine *e) {
     e->seg_start.release(); e->seg_end.release(); e->cnt.release(); e->cta_cnt.release(); e->cta_off.release();
     for (auto &b : e->ckeys) b.release();
     for (auto &b : e->cvals) b.release();
-    e->cell_off.release(); e->cpos.release(); e->cub_tmp.release();
+    e->cell_off.release(); e->cpos.release(); e->crank.release(); e->cell_cnt.release(); e->scan_tiles.release();
     e->aos.release(); e->fout.release(); e->render.release(); e->sx.release(); e->sy.release(); e->sz.release(); e->matrix.release(); e->flags.release(); e->diag.release();
     drop_graph(e);
     for (auto x : e->ev) cudaEventDestroy(x);

@@ -35,12 +35,25 @@ __device__ __forceinline__ int cell_axis(float x, const CellGrid g) {
     return min(max(c, 0), g.nc - 1);  // x == +W/2 lands in the last cell; NaN lands in cell 0
 }
 
-// keys[s] = linear cell index of slot s (ghosts: nc^3, sorted to the end); vals[s] = s.
-__global__ void __launch_bounds__(256) k_cell_keys(const float4 *__restrict__ pos, int n_slots, CellGrid g,
-                                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
-                                                   int *__restrict__ flag_to_clear) {
+// ---------------------------------------------------------------------------------------------
+// Sort by cell: a hand-written counting sort (count -> scan -> scatter -> order), the GPU analogue of the
+// reference's own counting sort over hash buckets (src/lib.rs:135-164: count, prefix sum, fill).
+//
+// `gate` (nullable): every kernel of the pipeline returns at once unless gate[0] == gate_value.  The all-pairs
+// path queues the pipeline behind its out-of-box flag, so that a device-resident run can hand a step with a
+// particle outside the box to the cell list without the host looking at the flag.
+#define P3D_GATED(gate, gate_value) \
+    if ((gate) != nullptr && (gate)[0] != (gate_value)) return
+
+// Pass 1.  keys[s] = linear cell index of slot s (ghosts: nc^3, a bin of their own after the last cell);
+// rank[s] = arrival order inside the cell (atomic: arbitrary, fixed up by pass 4); count[c] = population.
+__global__ void __launch_bounds__(256) k_cell_count(const float4 *__restrict__ pos, int n_slots, CellGrid g,
+                                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ rank,
+                                                    uint32_t *__restrict__ count, int *__restrict__ flag_to_clear,
+                                                    const int *__restrict__ gate, int gate_value) {
+    P3D_GATED(gate, gate_value);
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s == 0) *flag_to_clear = 0;
+    if (s == 0 && flag_to_clear) *flag_to_clear = 0;
     if (s >= n_slots) return;
     const float4 p = pos[s];
     uint32_t key = (uint32_t)(g.nc * g.nc * g.nc);
@@ -49,27 +62,142 @@ __global__ void __launch_bounds__(256) k_cell_keys(const float4 *__restrict__ po
         key = (uint32_t)((cz * g.nc + cy) * g.nc + cx);
     }
     keys[s] = key;
-    vals[s] = (uint32_t)s;
+    if (P3D_CELL_OK(key)) rank[s] = atomicAdd(count + key, 1u);
 }
 
-// After the sort: gather positions into cell order and build cell_off[c] = first sorted index whose
-// key is >= c, for c = 0 .. nc^3 (so cell c occupies [cell_off[c], cell_off[c+1]), empty cells included,
-// and cell_off[nc^3] is where the ghosts start).  The thread that sees a key change fills the gap.
-__global__ void __launch_bounds__(256) k_cell_gather(const float4 *__restrict__ pos, int n_slots,
-                                                     const uint32_t *__restrict__ keys_sorted,
-                                                     const uint32_t *__restrict__ vals_sorted,
-                                                     float4 *__restrict__ cpos, uint32_t *__restrict__ cell_off,
-                                                     uint32_t n_cells) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_slots) return;
-    const uint32_t key = keys_sorted[k];
-    if (P3D_SLOT_OK(vals_sorted[k])) cpos[k] = pos[vals_sorted[k]];
-    const uint32_t first = (k == 0) ? 0u : keys_sorted[k - 1] + 1u;
-    for (uint32_t c = first; c <= key; ++c)
-        if (P3D_CELL_OK(c)) cell_off[c] = (uint32_t)k;  // no iterations when the key repeats
-    if (k == n_slots - 1)
-        for (uint32_t c = key + 1u; c <= n_cells; ++c)
-            if (P3D_CELL_OK(c)) cell_off[c] = (uint32_t)n_slots;
+// Pass 2: exclusive prefix sum of count[0 .. L) -> off[0 .. L) in three launches (tile sums, scan of the tile
+// sums by one CTA, per-tile scan + offset).  off[c] = first sorted index of cell c; with L = nc^3 + 1 the last
+// entry, off[nc^3], is where the ghosts start.
+constexpr int kScanThreads = 1024;
+constexpr int kScanTile = 4 * kScanThreads;  // four consecutive counts per thread
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *warp_tot /* [32] shared */, uint32_t &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += a;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = warp_tot[lane];
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += a;
+        }
+        warp_tot[lane] = winc - w;                    // exclusive prefix of the warp totals
+        if (lane == 31) warp_tot[32] = winc;          // block total
+    }
+    __syncthreads();
+    total = warp_tot[32];
+    return warp_tot[warp] + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(const uint32_t *__restrict__ in, int L,
+                                                                 uint32_t *__restrict__ tile_sum,
+                                                                 const int *__restrict__ gate, int gate_value) {
+    P3D_GATED(gate, gate_value);
+    __shared__ uint32_t warp_tot[33];
+    const int base = blockIdx.x * kScanTile + 4 * threadIdx.x;
+    uint32_t v = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (base + k < L) v += in[base + k];
+    uint32_t total;
+    block_exclusive_scan(v, warp_tot, total);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_top(uint32_t *__restrict__ tile_sum, int n_tiles,
+                                                           const int *__restrict__ gate, int gate_value) {
+    P3D_GATED(gate, gate_value);
+    __shared__ uint32_t warp_tot[33];
+    uint32_t carry = 0u;
+    for (int base = 0; base < n_tiles; base += kScanThreads) {
+        const int t = base + threadIdx.x;
+        const uint32_t v = t < n_tiles ? tile_sum[t] : 0u;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, warp_tot, total);
+        if (t < n_tiles) tile_sum[t] = carry + ex;
+        carry += total;
+        __syncthreads();  // warp_tot is reused by the next trip
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const uint32_t *__restrict__ in, int L,
+                                                             const uint32_t *__restrict__ tile_off,
+                                                             uint32_t *__restrict__ out,
+                                                             const int *__restrict__ gate, int gate_value) {
+    P3D_GATED(gate, gate_value);
+    __shared__ uint32_t warp_tot[33];
+    const int base = blockIdx.x * kScanTile + 4 * threadIdx.x;
+    uint32_t c[4], v = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        c[k] = (base + k < L) ? in[base + k] : 0u;
+        v += c[k];
+    }
+    uint32_t total;
+    uint32_t at = tile_off[blockIdx.x] + block_exclusive_scan(v, warp_tot, total);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (base + k < L) out[base + k] = at;
+        at += c[k];
+    }
+}
+
+// Pass 3: slot s goes to position off[cell] + arrival rank (any order inside a cell).
+__global__ void __launch_bounds__(256) k_cell_scatter(int n_slots, const uint32_t *__restrict__ keys,
+                                                      const uint32_t *__restrict__ rank,
+                                                      const uint32_t *__restrict__ cell_off,
+                                                      uint32_t *__restrict__ members,
+                                                      const int *__restrict__ gate, int gate_value) {
+    P3D_GATED(gate, gate_value);
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    const uint32_t c = keys[s];
+    if (!P3D_CELL_OK(c)) return;
+    const uint32_t dst = cell_off[c] + rank[s];
+    if (P3D_SLOT_OK(dst)) members[dst] = (uint32_t)s;
+}
+
+// Pass 4: make the order inside every cell the slot order (a STABLE sort, hence the same forces bit for bit on every
+// run and on every rank), and gather keys / slots / positions into cell order.  A slot's stable rank is the number
+// of members of its cell with a smaller slot index: a handful of reads at ordinary densities.  Cells with more than
+// kStableMax members (and the ghost bin, whose entries are all alike) keep the arrival order: the force on a
+// particle is then still exact to rounding, only the summation order of such a cell may differ between runs.
+constexpr uint32_t kStableMax = 2048u;
+
+__global__ void __launch_bounds__(256) k_cell_order(const float4 *__restrict__ pos, int n_slots,
+                                                    const uint32_t *__restrict__ keys, const uint32_t *__restrict__ rank,
+                                                    const uint32_t *__restrict__ cell_off,
+                                                    const uint32_t *__restrict__ members, uint32_t n_cells,
+                                                    uint32_t *__restrict__ keys_sorted, uint32_t *__restrict__ vals_sorted,
+                                                    float4 *__restrict__ cpos,
+                                                    const int *__restrict__ gate, int gate_value) {
+    P3D_GATED(gate, gate_value);
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    const uint32_t c = keys[s];
+    if (!P3D_CELL_OK(c)) return;
+    const uint32_t lo = cell_off[c];
+    uint32_t r = rank[s];
+    if (c < n_cells) {
+        const uint32_t hi = P3D_SLOT_END_OK(cell_off[c + 1]) ? cell_off[c + 1] : lo;
+        if (hi - lo > 1u && hi - lo <= kStableMax) {
+            r = 0u;
+            for (uint32_t j = lo; j < hi; ++j) r += members[j] < (uint32_t)s;
+        }
+    }
+    const uint32_t dst = lo + r;
+    if (!P3D_SLOT_OK(dst)) return;
+    keys_sorted[dst] = c;
+    vals_sorted[dst] = (uint32_t)s;
+    cpos[dst] = pos[s];
 }
 
 // One candidate of the cell list: the reference's relative position (src/lib.rs:211-212) and the
@@ -124,86 +252,97 @@ __global__ void __launch_bounds__(kCellThreads) k_force_cells(const float4 *__re
                                                               const float *__restrict__ matrix,
                                                               const int *__restrict__ flags) {
     if ((flags[0] != 0) != GENERAL) return;  // the in-box and the general variant are both launched; one runs
+                                             // (the all-pairs path queues only the general one: its fallback)
     extern __shared__ float smat_dyn[];
     __shared__ uint32_t run_lo[kCellRuns][kCellThreads], run_hi[kCellRuns][kCellThreads];
     __shared__ uint8_t run_img[kCellRuns][kCellThreads];  // 2 bits per axis: 0 = offset 0, 1 = +W, 2 = -W
     for (int k = threadIdx.x; k < P.T * P.T; k += blockDim.x) smat_dyn[k] = matrix[k];
     __syncthreads();
-    const int k = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= i_end) return;
-    const uint32_t key = keys_sorted[k];
     const int nc = g.nc;
-    if (key >= (uint32_t)(nc * nc * nc)) return;  // ghost
-    const float4 pi = cpos[k];
-    const int cx = (int)(key % (uint32_t)nc), cy = (int)((key / (uint32_t)nc) % (uint32_t)nc),
-              cz = (int)(key / (uint32_t)(nc * nc));
-    const float *arow = smat_dyn + f2u(pi.w) * (uint32_t)P.T;
     const float c2 = P.c2, ncm = -P.c2 * P.m, nc2 = -P.c2, im = P.inv_m, r2 = P.r2;
     const int t = threadIdx.x;
+    // One particle per thread; the (rarely running) general variant is launched with a small grid and strides.
+    for (int k = i_begin + blockIdx.x * blockDim.x + threadIdx.x; k < i_end; k += gridDim.x * blockDim.x) {
+        const uint32_t key = keys_sorted[k];
+        if (key >= (uint32_t)(nc * nc * nc)) continue;  // ghost
+        const float4 pi = cpos[k];
+        const int cx = (int)(key % (uint32_t)nc), cy = (int)((key / (uint32_t)nc) % (uint32_t)nc),
+                  cz = (int)(key / (uint32_t)(nc * nc));
+        const float *arow = smat_dyn + f2u(pi.w) * (uint32_t)P.T;
 
-    int n_runs = 0;
+        int n_runs = 0;
 #pragma unroll
-    for (int dz = -1; dz <= 1; ++dz) {
-        int nz = cz + dz, iz = 0;
-        if (nz < 0) { nz += nc; iz = 1; } else if (nz >= nc) { nz -= nc; iz = 2; }
+        for (int dz = -1; dz <= 1; ++dz) {
+            int nz = cz + dz, iz = 0;
+            if (nz < 0) { nz += nc; iz = 1; } else if (nz >= nc) { nz -= nc; iz = 2; }
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-            int ny = cy + dy, iy = 0;
-            if (ny < 0) { ny += nc; iy = 1; } else if (ny >= nc) { ny -= nc; iy = 2; }
-            const uint32_t row = (uint32_t)((nz * nc + ny) * nc);
-            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, nc - 1);
-            run_lo[n_runs][t] = __ldg(cell_off + row + x0);
-            run_hi[n_runs][t] = __ldg(cell_off + row + x1 + 1);
-            run_img[n_runs][t] = (uint8_t)(iy << 2 | iz << 4);
-            ++n_runs;
-            if (cx == 0) {  // the -x neighbour is the last cell of the row; it sees us at x + W
-                run_lo[n_runs][t] = __ldg(cell_off + row + nc - 1);
-                run_hi[n_runs][t] = __ldg(cell_off + row + nc);
-                run_img[n_runs][t] = (uint8_t)(1 | iy << 2 | iz << 4);
+            for (int dy = -1; dy <= 1; ++dy) {
+                int ny = cy + dy, iy = 0;
+                if (ny < 0) { ny += nc; iy = 1; } else if (ny >= nc) { ny -= nc; iy = 2; }
+                const uint32_t row = (uint32_t)((nz * nc + ny) * nc);
+                const int x0 = max(cx - 1, 0), x1 = min(cx + 1, nc - 1);
+                run_lo[n_runs][t] = __ldg(cell_off + row + x0);
+                run_hi[n_runs][t] = __ldg(cell_off + row + x1 + 1);
+                run_img[n_runs][t] = (uint8_t)(iy << 2 | iz << 4);
                 ++n_runs;
-            } else if (cx == nc - 1) {
-                run_lo[n_runs][t] = __ldg(cell_off + row);
-                run_hi[n_runs][t] = __ldg(cell_off + row + 1);
-                run_img[n_runs][t] = (uint8_t)(2 | iy << 2 | iz << 4);
-                ++n_runs;
+                if (cx == 0) {  // the -x neighbour is the last cell of the row; it sees us at x + W
+                    run_lo[n_runs][t] = __ldg(cell_off + row + nc - 1);
+                    run_hi[n_runs][t] = __ldg(cell_off + row + nc);
+                    run_img[n_runs][t] = (uint8_t)(1 | iy << 2 | iz << 4);
+                    ++n_runs;
+                } else if (cx == nc - 1) {
+                    run_lo[n_runs][t] = __ldg(cell_off + row);
+                    run_hi[n_runs][t] = __ldg(cell_off + row + 1);
+                    run_img[n_runs][t] = (uint8_t)(2 | iy << 2 | iz << 4);
+                    ++n_runs;
+                }
             }
         }
-    }
-    // `position + offset` for offset = +W / -W (src/lib.rs:190-192), rounded like the reference
-    const float sx3[3] = {pi.x, __fadd_rn(pi.x, P.W), __fadd_rn(pi.x, -P.W)};
-    const float sy3[3] = {pi.y, __fadd_rn(pi.y, P.W), __fadd_rn(pi.y, -P.W)};
-    const float sz3[3] = {pi.z, __fadd_rn(pi.z, P.W), __fadd_rn(pi.z, -P.W)};
-    float ax = 0.f, ay = 0.f, az = 0.f;
-    int run = -1;
-    uint32_t j = 0, hi = 0;
-    float px = pi.x, py = pi.y, pz = pi.z;
-    for (;;) {
-        while (j >= hi) {  // next non-empty run
-            if (++run >= n_runs) goto done;
-            j = run_lo[run][t];
-            hi = run_hi[run][t];
-            if (!P3D_SLOT_END_OK(hi)) hi = j;  // (self-checking build only)
-            const int img = run_img[run][t];
-            const int ix = img & 3, iy = (img >> 2) & 3, iz = (img >> 4) & 3;
-            px = ix == 0 ? sx3[0] : (ix == 1 ? sx3[1] : sx3[2]);
-            py = iy == 0 ? sy3[0] : (iy == 1 ? sy3[1] : sy3[2]);
-            pz = iz == 0 ? sz3[0] : (iz == 1 ? sz3[1] : sz3[2]);
-        }
-        if (hi - j >= 8u) {  // long run (dense region): four candidates per trip, loads issued together
+        // `position + offset` for offset = +W / -W (src/lib.rs:190-192), rounded like the reference
+        const float sx3[3] = {pi.x, __fadd_rn(pi.x, P.W), __fadd_rn(pi.x, -P.W)};
+        const float sy3[3] = {pi.y, __fadd_rn(pi.y, P.W), __fadd_rn(pi.y, -P.W)};
+        const float sz3[3] = {pi.z, __fadd_rn(pi.z, P.W), __fadd_rn(pi.z, -P.W)};
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        int run = -1;
+        uint32_t j = 0, hi = 0;
+        float px = pi.x, py = pi.y, pz = pi.z;
+        for (;;) {
+            bool more = true;
+            while (j >= hi) {  // next non-empty run
+                if (++run >= n_runs) { more = false; break; }
+                j = run_lo[run][t];
+                hi = run_hi[run][t];
+                if (!P3D_SLOT_END_OK(hi)) hi = j;  // (self-checking build only)
+                const int img = run_img[run][t];
+                const int ix = img & 3, iy = (img >> 2) & 3, iz = (img >> 4) & 3;
+                px = ix == 0 ? sx3[0] : (ix == 1 ? sx3[1] : sx3[2]);
+                py = iy == 0 ? sy3[0] : (iy == 1 ? sy3[1] : sy3[2]);
+                pz = iz == 0 ? sz3[0] : (iz == 1 ? sz3[1] : sz3[2]);
+            }
+            if (!more) break;
+            // Up to four candidates per trip, their loads issued together (a run of three cells holds ~3 particles at
+            // density 1, so most runs are one trip); the candidates are evaluated in sorted order either way.
+            const uint32_t left = hi - j;
             float4 q[4];
+            if (left >= 4u) {  // long run (dense region): no predicates
 #pragma unroll
-            for (int u = 0; u < 4; ++u) q[u] = __ldg(cpos + j + u);
+                for (int u = 0; u < 4; ++u) q[u] = __ldg(cpos + j + u);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                cell_pair<RCUT, GENERAL>(q[u], px, py, pz, sx3, sy3, sz3, arow, c2, ncm, nc2, im, r2, ax, ay, az);
-            j += 4;
-            continue;
+                for (int u = 0; u < 4; ++u)
+                    cell_pair<RCUT, GENERAL>(q[u], px, py, pz, sx3, sy3, sz3, arow, c2, ncm, nc2, im, r2, ax, ay, az);
+                j += 4;
+                continue;
+            }
+#pragma unroll
+            for (int u = 0; u < 3; ++u) q[u] = __ldg(cpos + j + (u < (int)left ? u : 0));
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+                if (u < (int)left)
+                    cell_pair<RCUT, GENERAL>(q[u], px, py, pz, sx3, sy3, sz3, arow, c2, ncm, nc2, im, r2, ax, ay, az);
+            j = hi;
         }
-        cell_pair<RCUT, GENERAL>(__ldg(cpos + j), px, py, pz, sx3, sy3, sz3, arow, c2, ncm, nc2, im, r2, ax, ay, az);
-        ++j;
+        if (P3D_SLOT_OK(vals_sorted[k])) frc[vals_sorted[k]] = make_float4(ax, ay, az, 0.f);
     }
-done:
-    if (P3D_SLOT_OK(vals_sorted[k])) frc[vals_sorted[k]] = make_float4(ax, ay, az, 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -117,8 +117,8 @@ enum p3d_force_kernel {
     P3D_FORCE_AUTO = 0,      /* CELLS for n >= 192 (all-pairs when the box is narrower than three cells), else REFERENCE_ORDER */
     P3D_FORCE_REFERENCE_ORDER = 1, /* one thread per particle, exact sqrt/div, all three images per axis */
     P3D_FORCE_PAIR = 2,      /* symmetric block-pair kernel, packed FP32x2, rsqrt (all N^2 pairs); a step whose input has a
-                              * particle outside the box is evaluated by the exact kernel (1) instead or, in a single-step
-                              * call from 32,768 particles, by the cell list (3): same forces */
+                              * particle outside the box is evaluated by the exact kernel (1) instead or, from 32,768
+                              * particles, by the cell list (3), queued behind a device-side flag: same forces */
     P3D_FORCE_CELLS = 3      /* uniform-grid cell list: the GPU analogue of the reference's spatial hash
                                 (src/lib.rs:135-236); same results, O(N * neighbours) work */
 };

@@ -182,6 +182,8 @@ if __name__ == "__main__":
                     t0 = time.time(); eng.step(P, 1 / 60, 400); eng.sync(); dt = (time.time() - t0) / 400
                     print(f"graph={graph} n={n} kernel={kernel}: {dt*1e6:.1f} us/step", flush=True)
                     eng.close()
+    if "cells1m" in what:
+        timing(1048576, 101.6, _abi.FORCE_CELLS, steps=5)
     if "cells" in what:
         timing(1000, 10.0, _abi.FORCE_CELLS, steps=50)
         timing(16384, 25.4, _abi.FORCE_CELLS, steps=50)
