@@ -91,7 +91,9 @@ struct p3d_engine {
     int B_next = 0;      // block size for the next upload (P3D_OPT_BLOCK_SIZE); 0 = by particle count
     int M = 0;           // n_slots / B
     uint32_t T = 0;      // id_count the layout was built for
-    bool typed = false;  // slots are grouped by type (needed by the pair kernel); false: slot = caller index
+    bool typed = false;  // slots are grouped by type (needed by the pair kernel); false: slot = caller index ...
+    bool permuted = false;   // ... unless the identity layout was re-slotted into cell order (reslot_by_cell)
+    int steps_since_reslot = 0;
     std::vector<int> seg_start_h, seg_end_h;
 
     DevBuf<float4> pos[2], vel, frc, spos;
@@ -101,7 +103,8 @@ struct p3d_engine {
     DevBuf<int2> cta_cnt, cta_off;
     // cell-list path
     DevBuf<uint32_t> ckeys[2], cvals[2], crank, cell_cnt, cell_off, scan_tiles;
-    DevBuf<float4> cpos;
+    DevBuf<uint32_t> caller_of, caller_tmp;  // slot -> caller index of a re-slotted identity layout
+    DevBuf<float4> cpos, vel_tmp;
     DevBuf<float> aos, fout, sx, sy, sz;
     DevBuf<float4> render;
     DevBuf<float> matrix;
@@ -210,6 +213,9 @@ int ensure_common(p3d_engine *e, size_t n, size_t ns) {
 
 int resolve_force_kernel_for(const p3d_engine *e, size_t n);
 
+// caller index -> slot table, or null when slot == caller index
+const uint32_t *slot_map(const p3d_engine *e) { return (e->typed || e->permuted) ? e->slot_of.p : nullptr; }
+
 // A sharded engine computes PARTIAL forces (its block rows) and integrates only its slot range; between the two
 // the driver has to sum the forces and afterwards gather the positions.  A whole-step call would silently
 // integrate with partial forces, so it is refused.
@@ -248,6 +254,7 @@ int build_layout_identity(p3d_engine *e, size_t n, uint32_t T) {
     e->n = n;
     e->T = T;
     e->typed = false;
+    e->permuted = false;
     e->layout_version++;
     CU(cudaMemsetAsync(e->flags.p, 0, 4 * sizeof(int), e->stream));
     return P3D_OK;
@@ -331,6 +338,7 @@ int layout_finish(p3d_engine *e, size_t n, uint32_t T) {
     if ((rc = e->diag.ensure(8))) return rc;
     // every allocation succeeded: only now does the engine's layout change
     e->typed = true;
+    e->permuted = false;
     e->layout_version++;
     e->B = B;
     e->seg_start_h = seg_start;
@@ -435,10 +443,52 @@ int build_cells(p3d_engine *e, const DevParams &P, const float4 *pos, int *flag_
     k_scan_apply<<<tiles, kScanThreads, 0, st>>>(e->cell_cnt.p, L, e->scan_tiles.p, e->cell_off.p, gate, gate_value);
     k_cell_scatter<<<grid, 256, 0, st>>>(ns, e->ckeys[0].p, e->crank.p, e->cell_off.p, e->cvals[0].p, gate, gate_value);
     k_cell_order<<<grid, 256, 0, st>>>(pos, ns, e->ckeys[0].p, e->crank.p, e->cell_off.p, e->cvals[0].p, (uint32_t)ncell,
-                                       e->ckeys[1].p, e->cvals[1].p, e->cpos.p, gate, gate_value);
+                                       e->permuted ? e->caller_of.p : nullptr, e->ckeys[1].p, e->cvals[1].p, e->cpos.p,
+                                       gate, gate_value);
     e->counters[0] += 6;
     CU(cudaGetLastError());
     return P3D_OK;
+}
+
+// Re-slots an identity layout into cell order (device-resident cell-list runs).  The caller's particles arrive in
+// arbitrary spatial order, so every per-step pass of the cell sort (the count atomics, the scatter, the gather) and
+// the force kernel's final scatter would touch memory at random; once the SLOTS follow the cells, and for as long as
+// the particles have not drifted far, those accesses are nearly sequential.  Pure data movement: positions,
+// velocities and the caller<->slot tables are permuted in place (same buffers: pointers held by CUDA graphs stay
+// valid), and the order of the candidates inside a cell is the caller order either way (k_cell_order), so the
+// forces - and with them every later state - are bit for bit those of the un-permuted layout.
+constexpr int kReslotMin = 32768;   // particles from which re-slotting pays
+constexpr int kReslotEvery = 32;    // steps between two re-slots of a long run
+
+int reslot_by_cell(p3d_engine *e, const DevParams &P) {
+    cudaStream_t st = e->stream;
+    const int ns = e->n_slots;
+    CellGrid g;
+    int rc;
+    if ((rc = e->vel_tmp.ensure((size_t)ns))) return rc;
+    if ((rc = e->caller_of.ensure((size_t)ns))) return rc;
+    if ((rc = e->caller_tmp.ensure((size_t)ns))) return rc;
+    if ((rc = e->slot_of.ensure(std::max<size_t>(e->n, 1)))) return rc;
+    if ((rc = build_cells(e, P, e->pos[e->cur].p, e->flags.p + 3, g))) return rc;
+    if (g.nc < 3) return P3D_OK;
+    k_reslot<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(ns, (int)e->n, e->cvals[1].p, e->vel.p,
+                                                          e->permuted ? e->caller_of.p : nullptr, e->vel_tmp.p,
+                                                          e->caller_tmp.p, e->slot_of.p);
+    e->counters[0]++;
+    CU(cudaGetLastError());
+    const size_t bytes = (size_t)ns * sizeof(float4);
+    CU(cudaMemcpyAsync(e->pos[e->cur].p, e->cpos.p, bytes, cudaMemcpyDeviceToDevice, st));      // cpos[k] = pos[old slot of k]
+    CU(cudaMemcpyAsync(e->pos[e->cur ^ 1].p, e->cpos.p, bytes, cudaMemcpyDeviceToDevice, st));  // ghosts line up in both
+    CU(cudaMemcpyAsync(e->vel.p, e->vel_tmp.p, bytes, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(e->caller_of.p, e->caller_tmp.p, (size_t)ns * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    e->permuted = true;
+    e->steps_since_reslot = 0;
+    return P3D_OK;
+}
+
+bool reslot_applies(const p3d_engine *e) {
+    return !e->typed && e->world == 1 && !e->is_member && e->n >= (size_t)kReslotMin &&
+           resolve_force_kernel(e) == P3D_FORCE_CELLS;
 }
 
 // K5: adds the reference's double-visit contributions to the ideal forces already in frc.
@@ -722,13 +772,13 @@ void drop_graph(p3d_engine *e) {
 
 // Everything a captured pair of steps depends on; any change forces a re-capture.
 std::vector<unsigned char> make_graph_key(const p3d_engine *e, const DevParams &P, float ts) {
-    std::vector<unsigned char> k(sizeof(DevParams) + sizeof(float) + 8 * sizeof(uint64_t));
+    std::vector<unsigned char> k(sizeof(DevParams) + sizeof(float) + 9 * sizeof(uint64_t));
     unsigned char *p = k.data();
     std::memcpy(p, &P, sizeof(DevParams)); p += sizeof(DevParams);
     std::memcpy(p, &ts, sizeof(float)); p += sizeof(float);
-    const uint64_t v[8] = {e->layout_version, (uint64_t)e->cur, (uint64_t)e->parity, (uint64_t)resolve_force_kernel(e),
+    const uint64_t v[9] = {e->layout_version, (uint64_t)e->cur, (uint64_t)e->parity, (uint64_t)resolve_force_kernel(e),
                            (uint64_t)e->opt_faithful, (uint64_t)e->opt_block_sort, (uint64_t)(uintptr_t)e->stream,
-                           (uint64_t)e->rank * 64 + (uint64_t)e->world};
+                           (uint64_t)e->rank * 64 + (uint64_t)e->world, (uint64_t)e->permuted};
     std::memcpy(p, v, sizeof(v));
     return k;
 }
@@ -772,25 +822,37 @@ int run_steps(p3d_engine *e, const p3d_params *prm, const DevParams &P, float ts
     if ((rc = check_box_now(e, P))) return rc;  // world_size may have changed since the last call
     e->timed_steps = 0;
     if (e->opt_timing && (rc = ensure_events(e, n_steps))) return rc;
+    // device-resident cell-list runs keep their slots in cell order (see reslot_by_cell)
+    const bool reslot = reslot_applies(e) && n_steps >= 2;
+    auto maybe_reslot = [&]() -> int {
+        if (reslot && (!e->permuted || e->steps_since_reslot >= kReslotEvery)) return reslot_by_cell(e, P);
+        return P3D_OK;
+    };
+    if ((rc = maybe_reslot())) return rc;
     int s = 0;
     // Long untimed runs replay a two-step CUDA graph: a step is 8-15 launches, and at small N their
     // launch latency is the whole step time.
     if (e->opt_graph && !e->opt_timing && n_steps >= 6) {
         for (; s < 2; ++s)
             if ((rc = one_step(e, P, ts, false, s))) return rc;  // allocates every lazily created buffer
+        e->steps_since_reslot += 2;
         if (!e->graph_exec || e->graph_key != make_graph_key(e, P, ts)) {
             if (capture_two_steps(e, P, ts) != P3D_OK) drop_graph(e);  // fall back to ordinary launches
         }
         if (e->graph_exec) {
             for (; s + 2 <= n_steps; s += 2) {
+                if ((rc = maybe_reslot())) return rc;  // same buffers, same pointers: the graph stays valid
                 CU(cudaGraphLaunch(e->graph_exec, e->stream));
                 for (int k = 0; k < 3; ++k) e->counters[k] += e->graph_launches[k];
+                e->steps_since_reslot += 2;
             }
         }
     }
     for (; s < n_steps; ++s) {
         const bool timed = e->opt_timing && s < kMaxTimedSteps;
+        if ((rc = maybe_reslot())) return rc;
         if ((rc = one_step(e, P, ts, timed, s))) return rc;
+        e->steps_since_reslot++;
     }
     return P3D_OK;
 }
@@ -898,7 +960,7 @@ void p3d_destroy(p3d_engine *e) {
     e->seg_start.release(); e->seg_end.release(); e->cnt.release(); e->cta_cnt.release(); e->cta_off.release();
     for (auto &b : e->ckeys) b.release();
     for (auto &b : e->cvals) b.release();
-    e->cell_off.release(); e->cpos.release(); e->crank.release(); e->cell_cnt.release(); e->scan_tiles.release();
+    e->cell_off.release(); e->cpos.release(); e->crank.release(); e->cell_cnt.release(); e->scan_tiles.release(); e->caller_of.release(); e->caller_tmp.release(); e->vel_tmp.release();
     e->aos.release(); e->fout.release(); e->render.release(); e->sx.release(); e->sy.release(); e->sz.release(); e->matrix.release(); e->flags.release(); e->diag.release();
     drop_graph(e);
     for (auto x : e->ev) cudaEventDestroy(x);
@@ -1085,7 +1147,7 @@ static int download_range(p3d_engine *e, p3d_particle *out_part, size_t i_begin,
     }
     if (cnt) {
         k_unpack<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(e->pos[e->cur].p, e->vel.p,
-                                                                       e->typed ? e->slot_of.p : nullptr, e->aos.p,
+                                                                       slot_map(e), e->aos.p,
                                                                        (int)i_begin, (int)i_end);
         e->counters[0]++;
         CU(cudaGetLastError());
@@ -1139,7 +1201,7 @@ int p3d_download_render(p3d_engine *e, float world_size, void *out, size_t out_b
     int rc;
     if ((rc = e->render.ensure(2 * n))) return rc;
     k_unpack_render<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->pos[e->cur].p, e->vel.p,
-                                                                        e->typed ? e->slot_of.p : nullptr,
+                                                                        slot_map(e),
                                                                         e->render.p, (int)n);
     e->counters[0]++;
     CU(cudaGetLastError());
@@ -1157,7 +1219,7 @@ int p3d_download_forces(p3d_engine *e, float *out_xyz, size_t n) {
     CU(cudaSetDevice(e->device));
     int rc;
     if ((rc = e->fout.ensure(n * 3))) return rc;
-    k_unpack_forces<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->frc.p, e->typed ? e->slot_of.p : nullptr,
+    k_unpack_forces<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->frc.p, slot_map(e),
                                                                         e->fout.p, (int)n);
     e->counters[0]++;
     CU(cudaGetLastError());
@@ -1429,7 +1491,7 @@ int p3d_slot_of(p3d_engine *e, uint32_t *out, size_t n) {
     if (!n) return P3D_OK;
     if (!out) return fail(P3D_ERR_INVALID, "out is null");
     CU(cudaSetDevice(e->device));
-    if (e->typed) {
+    if (slot_map(e)) {
         CU(cudaMemcpyAsync(out, e->slot_of.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
         CU(cudaStreamSynchronize(e->stream));
     } else {
@@ -1637,7 +1699,7 @@ static int multi_download_forces(p3d_engine *grp, float *out_xyz, size_t n) {
     if ((rc = e->fout.ensure(n * 3))) return rc;
     PeerForces pf;
     for (int g = 0; g < 8; ++g) pf.frc[g] = g < G ? grp->members[g]->frc.p : nullptr;
-    k_unpack_forces_sum<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(pf, G, e->typed ? e->slot_of.p : nullptr,
+    k_unpack_forces_sum<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(pf, G, slot_map(e),
                                                                             e->fout.p, (int)n);
     e->counters[0]++;
     CU(cudaGetLastError());

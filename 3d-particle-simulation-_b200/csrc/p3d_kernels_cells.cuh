@@ -165,9 +165,10 @@ __global__ void __launch_bounds__(256) k_cell_scatter(int n_slots, const uint32_
     if (P3D_SLOT_OK(dst)) members[dst] = (uint32_t)s;
 }
 
-// Pass 4: make the order inside every cell the slot order (a STABLE sort, hence the same forces bit for bit on every
-// run and on every rank), and gather keys / slots / positions into cell order.  A slot's stable rank is the number
-// of members of its cell with a smaller slot index: a handful of reads at ordinary densities.  Cells with more than
+// Pass 4: make the order inside every cell the CALLER order (a stable sort by the caller's particle index, hence the
+// same forces bit for bit on every run, on every rank and whatever the slot permutation, see reslot_by_cell), and
+// gather keys / slots / positions into cell order.  A slot's rank is the number of members of its cell with a
+// smaller caller index (caller_of == nullptr: slot == caller index): a handful of reads at ordinary densities.  Cells with more than
 // kStableMax members (and the ghost bin, whose entries are all alike) keep the arrival order: the force on a
 // particle is then still exact to rounding, only the summation order of such a cell may differ between runs.
 constexpr uint32_t kStableMax = 2048u;
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(256) k_cell_order(const float4 *__restrict__ p
                                                     const uint32_t *__restrict__ keys, const uint32_t *__restrict__ rank,
                                                     const uint32_t *__restrict__ cell_off,
                                                     const uint32_t *__restrict__ members, uint32_t n_cells,
+                                                    const uint32_t *__restrict__ caller_of,
                                                     uint32_t *__restrict__ keys_sorted, uint32_t *__restrict__ vals_sorted,
                                                     float4 *__restrict__ cpos,
                                                     const int *__restrict__ gate, int gate_value) {
@@ -190,7 +192,15 @@ __global__ void __launch_bounds__(256) k_cell_order(const float4 *__restrict__ p
         const uint32_t hi = P3D_SLOT_END_OK(cell_off[c + 1]) ? cell_off[c + 1] : lo;
         if (hi - lo > 1u && hi - lo <= kStableMax) {
             r = 0u;
-            for (uint32_t j = lo; j < hi; ++j) r += members[j] < (uint32_t)s;
+            if (caller_of) {
+                const uint32_t me = caller_of[s];
+                for (uint32_t j = lo; j < hi; ++j) {
+                    const uint32_t o = members[j];
+                    if (P3D_SLOT_OK(o)) r += caller_of[o] < me;
+                }
+            } else {
+                for (uint32_t j = lo; j < hi; ++j) r += members[j] < (uint32_t)s;
+            }
         }
     }
     const uint32_t dst = lo + r;
@@ -198,6 +208,22 @@ __global__ void __launch_bounds__(256) k_cell_order(const float4 *__restrict__ p
     keys_sorted[dst] = c;
     vals_sorted[dst] = (uint32_t)s;
     cpos[dst] = pos[s];
+}
+
+// Re-slotting (reslot_by_cell): sorted position k takes over the particle of old slot vals_sorted[k].  Positions were
+// already gathered by k_cell_order (cpos); this moves the velocities and rewrites both index tables.
+__global__ void __launch_bounds__(256) k_reslot(int n_slots, int n, const uint32_t *__restrict__ vals_sorted,
+                                                const float4 *__restrict__ vel, const uint32_t *__restrict__ caller_of,
+                                                float4 *__restrict__ vel_new, uint32_t *__restrict__ caller_new,
+                                                uint32_t *__restrict__ slot_of) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_slots) return;
+    const uint32_t old = vals_sorted[k];
+    if (!P3D_SLOT_OK(old)) return;
+    vel_new[k] = vel[old];
+    const uint32_t caller = caller_of ? caller_of[old] : (old < (uint32_t)n ? old : P3D_GHOST_ID);
+    caller_new[k] = caller;
+    if (caller != P3D_GHOST_ID && caller < (uint32_t)n) slot_of[caller] = (uint32_t)k;
 }
 
 // One candidate of the cell list: the reference's relative position (src/lib.rs:211-212) and the
@@ -234,16 +260,28 @@ __device__ __forceinline__ void cell_pair(const float4 q, float px, float py, fl
 
 // One thread per particle in cell order.  i_begin/i_end shard the sorted range across GPUs.
 //
-// The candidates of a particle are up to 18 contiguous runs of the sorted array: for each of the 9
-// (dy,dz) rows the cells cx-1..cx+1 that do not wrap form ONE run (cells are x-fastest), plus one
-// single-cell run when the row wraps through an x face.  The runs are written to shared memory and
-// consumed by a single flat loop, so a warp iterates max-over-lanes(total candidates) times instead of
-// sum-over-cells(max-over-lanes(cell population)) — with ~1 particle per cell that is ~40 vs ~100.
+// The candidates of a particle are up to 18 contiguous runs of the sorted array: for each of the 9 (dy,dz) rows the
+// cells cx-1..cx+1 that do not wrap form ONE run (cells are x-fastest), plus one single-cell run when the row wraps
+// through an x face.  ncu on the earlier per-run loops: instruction-issue bound, 12-15 of 32 lanes active, and most
+// of the instructions were RUN SWITCHES executed for a few lanes at a time (every lane exhausts its ~3-candidate
+// runs on different trips).  Hence two phases:
+//   A  all lanes walk the 9 rows together (uniform control flow: the offsets of a row are loaded by every lane at the
+//      same time) and write the sorted indices of their candidates into a per-thread list in shared memory;
+//   B  one flat loop over the list: one candidate per trip, the next one already in flight; a warp iterates
+//      max-over-lanes(total candidates) times, ~40 at density 1 against a mean of 27, with no control flow inside.
+// Lanes in a y/z face row (their rows wrap, the image differs per row), lanes whose list would overflow (dense
+// regions: long runs amortise the switches anyway) and the GENERAL variant take the direct per-run loop instead.
+// The candidate ORDER is the same in both paths and the same as before (rows z-major, the wrap cell after the row's
+// main run), so the forces do not depend on which path a lane takes.
 constexpr int kCellThreads = 128;
-constexpr int kCellRuns = 18;
+// 48 entries (24 KB per CTA) with 8 resident CTAs per SM measured best on the B200 at N = 1M, density 1 (candidates per
+// particle ~ Poisson(27)): 0.179 ms per step against 0.184 (64 entries, 6 CTAs) and 0.207 (40 entries, 10 CTAs, spills)
+constexpr int kCellList = 48;                 // list entries per thread
+constexpr int kCellMinBlocks = 8;
+constexpr uint32_t kCellWrapBit = 0x80000000u;  // list entry: candidate seen through the x face
 
 template <bool RCUT, bool GENERAL>
-__global__ void __launch_bounds__(kCellThreads) k_force_cells(const float4 *__restrict__ cpos,
+__global__ void __launch_bounds__(kCellThreads, kCellMinBlocks) k_force_cells(const float4 *__restrict__ cpos,
                                                               const uint32_t *__restrict__ keys_sorted,
                                                               const uint32_t *__restrict__ vals_sorted,
                                                               const uint32_t *__restrict__ cell_off, int n_slots,
@@ -254,13 +292,12 @@ __global__ void __launch_bounds__(kCellThreads) k_force_cells(const float4 *__re
     if ((flags[0] != 0) != GENERAL) return;  // the in-box and the general variant are both launched; one runs
                                              // (the all-pairs path queues only the general one: its fallback)
     extern __shared__ float smat_dyn[];
-    __shared__ uint32_t run_lo[kCellRuns][kCellThreads], run_hi[kCellRuns][kCellThreads];
-    __shared__ uint8_t run_img[kCellRuns][kCellThreads];  // 2 bits per axis: 0 = offset 0, 1 = +W, 2 = -W
+    __shared__ uint32_t cand[GENERAL ? 1 : kCellList][kCellThreads];
     for (int k = threadIdx.x; k < P.T * P.T; k += blockDim.x) smat_dyn[k] = matrix[k];
     __syncthreads();
     const int nc = g.nc;
-    const float c2 = P.c2, ncm = -P.c2 * P.m, nc2 = -P.c2, im = P.inv_m, r2 = P.r2;
     const int t = threadIdx.x;
+    const float c2 = P.c2, ncm = -P.c2 * P.m, nc2 = -P.c2, im = P.inv_m, r2 = P.r2;
     // One particle per thread; the (rarely running) general variant is launched with a small grid and strides.
     for (int k = i_begin + blockIdx.x * blockDim.x + threadIdx.x; k < i_end; k += gridDim.x * blockDim.x) {
         const uint32_t key = keys_sorted[k];
@@ -269,77 +306,83 @@ __global__ void __launch_bounds__(kCellThreads) k_force_cells(const float4 *__re
         const int cx = (int)(key % (uint32_t)nc), cy = (int)((key / (uint32_t)nc) % (uint32_t)nc),
                   cz = (int)(key / (uint32_t)(nc * nc));
         const float *arow = smat_dyn + f2u(pi.w) * (uint32_t)P.T;
-
-        int n_runs = 0;
-#pragma unroll
-        for (int dz = -1; dz <= 1; ++dz) {
-            int nz = cz + dz, iz = 0;
-            if (nz < 0) { nz += nc; iz = 1; } else if (nz >= nc) { nz -= nc; iz = 2; }
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
-                int ny = cy + dy, iy = 0;
-                if (ny < 0) { ny += nc; iy = 1; } else if (ny >= nc) { ny -= nc; iy = 2; }
-                const uint32_t row = (uint32_t)((nz * nc + ny) * nc);
-                const int x0 = max(cx - 1, 0), x1 = min(cx + 1, nc - 1);
-                run_lo[n_runs][t] = __ldg(cell_off + row + x0);
-                run_hi[n_runs][t] = __ldg(cell_off + row + x1 + 1);
-                run_img[n_runs][t] = (uint8_t)(iy << 2 | iz << 4);
-                ++n_runs;
-                if (cx == 0) {  // the -x neighbour is the last cell of the row; it sees us at x + W
-                    run_lo[n_runs][t] = __ldg(cell_off + row + nc - 1);
-                    run_hi[n_runs][t] = __ldg(cell_off + row + nc);
-                    run_img[n_runs][t] = (uint8_t)(1 | iy << 2 | iz << 4);
-                    ++n_runs;
-                } else if (cx == nc - 1) {
-                    run_lo[n_runs][t] = __ldg(cell_off + row);
-                    run_hi[n_runs][t] = __ldg(cell_off + row + 1);
-                    run_img[n_runs][t] = (uint8_t)(2 | iy << 2 | iz << 4);
-                    ++n_runs;
-                }
-            }
-        }
         // `position + offset` for offset = +W / -W (src/lib.rs:190-192), rounded like the reference
         const float sx3[3] = {pi.x, __fadd_rn(pi.x, P.W), __fadd_rn(pi.x, -P.W)};
         const float sy3[3] = {pi.y, __fadd_rn(pi.y, P.W), __fadd_rn(pi.y, -P.W)};
         const float sz3[3] = {pi.z, __fadd_rn(pi.z, P.W), __fadd_rn(pi.z, -P.W)};
+        const bool x_edge = (cx == 0) || (cx == nc - 1);
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, nc - 1);
+        const int xw = (cx == 0) ? nc - 1 : 0;             // the cell behind the x face (edge cells only) ...
+        const float pxw = (cx == 0) ? sx3[1] : sx3[2];     // ... sees us at x + W resp. x - W
         float ax = 0.f, ay = 0.f, az = 0.f;
-        int run = -1;
-        uint32_t j = 0, hi = 0;
-        float px = pi.x, py = pi.y, pz = pi.z;
-        for (;;) {
-            bool more = true;
-            while (j >= hi) {  // next non-empty run
-                if (++run >= n_runs) { more = false; break; }
-                j = run_lo[run][t];
-                hi = run_hi[run][t];
+
+        bool direct = GENERAL || cy == 0 || cy == nc - 1 || cz == 0 || cz == nc - 1;
+        if (!GENERAL) {
+            // ---- phase A: candidate list (interior rows: no y/z wrap, so a row is plain index arithmetic) ----
+            int cnt = 0;
+            if (!direct) {
+                const uint32_t centre = (uint32_t)((cz * nc + cy) * nc);
+#pragma unroll
+                for (int row9 = 0; row9 < 9; ++row9) {
+                    const int dz = row9 / 3 - 1, dy = row9 % 3 - 1;
+                    const uint32_t row = centre + (uint32_t)((dz * nc + dy) * nc);
+                    uint32_t j = __ldg(cell_off + row + x0);
+                    uint32_t hi = __ldg(cell_off + row + x1 + 1);
+                    if (!P3D_SLOT_END_OK(hi)) hi = j;  // (self-checking build only)
+                    if (cnt + (int)(hi - j) > kCellList) { direct = true; break; }
+                    for (; j < hi; ++j) cand[cnt++][t] = j;
+                    if (x_edge) {
+                        uint32_t jw = __ldg(cell_off + row + xw), hw = __ldg(cell_off + row + xw + 1);
+                        if (!P3D_SLOT_END_OK(hw)) hw = jw;
+                        if (cnt + (int)(hw - jw) > kCellList) { direct = true; break; }
+                        for (; jw < hw; ++jw) cand[cnt++][t] = jw | kCellWrapBit;
+                    }
+                }
+            }
+            // ---- phase B: flat loop over the list, the next candidate's load issued before this one is evaluated ----
+            if (!direct && cnt > 0) {
+                uint32_t e = cand[0][t];
+                float4 q = __ldg(cpos + (e & ~kCellWrapBit));
+                for (int i = 0; i < cnt; ++i) {
+                    const uint32_t e_next = cand[min(i + 1, cnt - 1)][t];
+                    const float4 q_next = __ldg(cpos + (e_next & ~kCellWrapBit));
+                    const float px = (e & kCellWrapBit) ? pxw : pi.x;
+                    cell_pair<RCUT, false>(q, px, pi.y, pi.z, sx3, sy3, sz3, arow, c2, ncm, nc2, im, r2, ax, ay, az);
+                    e = e_next;
+                    q = q_next;
+                }
+            }
+        }
+        if (direct) {
+            // ---- direct per-run loop: run 2*row = the non-wrapping cells of row (dy,dz), run 2*row + 1 = the cell
+            //      behind the x face (edge cells only); four candidates per trip while a run lasts ----
+            ax = ay = az = 0.f;
+            for (int run = 0; run < 18; ++run) {
+                const bool wrap = run & 1;
+                if (wrap && !x_edge) continue;
+                const int row9 = run >> 1;
+                const int dz = row9 / 3 - 1, dy = row9 - (row9 / 3) * 3 - 1;
+                int nz = cz + dz, ny = cy + dy;
+                float pz = sz3[0], py = sy3[0];
+                if (nz < 0) { nz += nc; pz = sz3[1]; } else if (nz >= nc) { nz -= nc; pz = sz3[2]; }
+                if (ny < 0) { ny += nc; py = sy3[1]; } else if (ny >= nc) { ny -= nc; py = sy3[2]; }
+                const uint32_t row = (uint32_t)((nz * nc + ny) * nc);
+                const uint32_t c_lo = wrap ? (uint32_t)xw : (uint32_t)x0, c_hi = wrap ? (uint32_t)xw : (uint32_t)x1;
+                uint32_t j = __ldg(cell_off + row + c_lo);
+                uint32_t hi = __ldg(cell_off + row + c_hi + 1);
                 if (!P3D_SLOT_END_OK(hi)) hi = j;  // (self-checking build only)
-                const int img = run_img[run][t];
-                const int ix = img & 3, iy = (img >> 2) & 3, iz = (img >> 4) & 3;
-                px = ix == 0 ? sx3[0] : (ix == 1 ? sx3[1] : sx3[2]);
-                py = iy == 0 ? sy3[0] : (iy == 1 ? sy3[1] : sy3[2]);
-                pz = iz == 0 ? sz3[0] : (iz == 1 ? sz3[1] : sz3[2]);
+                const float px = wrap ? pxw : sx3[0];
+                for (; j + 4u <= hi; j += 4u) {
+                    float4 q[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) q[u] = __ldg(cpos + j + u);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        cell_pair<RCUT, GENERAL>(q[u], px, py, pz, sx3, sy3, sz3, arow, c2, ncm, nc2, im, r2, ax, ay, az);
+                }
+                for (; j < hi; ++j)
+                    cell_pair<RCUT, GENERAL>(__ldg(cpos + j), px, py, pz, sx3, sy3, sz3, arow, c2, ncm, nc2, im, r2, ax, ay, az);
             }
-            if (!more) break;
-            // Up to four candidates per trip, their loads issued together (a run of three cells holds ~3 particles at
-            // density 1, so most runs are one trip); the candidates are evaluated in sorted order either way.
-            const uint32_t left = hi - j;
-            float4 q[4];
-            if (left >= 4u) {  // long run (dense region): no predicates
-#pragma unroll
-                for (int u = 0; u < 4; ++u) q[u] = __ldg(cpos + j + u);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    cell_pair<RCUT, GENERAL>(q[u], px, py, pz, sx3, sy3, sz3, arow, c2, ncm, nc2, im, r2, ax, ay, az);
-                j += 4;
-                continue;
-            }
-#pragma unroll
-            for (int u = 0; u < 3; ++u) q[u] = __ldg(cpos + j + (u < (int)left ? u : 0));
-#pragma unroll
-            for (int u = 0; u < 3; ++u)
-                if (u < (int)left)
-                    cell_pair<RCUT, GENERAL>(q[u], px, py, pz, sx3, sy3, sz3, arow, c2, ncm, nc2, im, r2, ax, ay, az);
-            j = hi;
         }
         if (P3D_SLOT_OK(vals_sorted[k])) frc[vals_sorted[k]] = make_float4(ax, ay, az, 0.f);
     }

@@ -519,6 +519,50 @@ def test_graph_replay_matches_ordinary_launches(default_params, kernel):
         assert outs[0].tobytes() == outs[1].tobytes()
 
 
+# ---------------------------------------------------------------- cell-order re-slotting (device-resident cell list)
+@pytest.mark.parametrize("graph", [1, 0], ids=["graph", "launches"])
+@pytest.mark.parametrize("plummer", [False, True], ids=["uniform", "plummer"])
+def test_cell_order_reslot_is_bitwise_transparent(default_params, graph, plummer):
+    """From 32,768 particles a device-resident cell-list run keeps its SLOTS in cell order (reslot_by_cell, every 32
+    steps): pure data movement.  70 resident steps must equal 70 x p3d_update (fresh upload each time, never
+    re-slotted) bit for bit, in the caller's index order, and the caller -> slot table must be a permutation."""
+    n, W, steps = 100000, 46.4, 70
+    prm = dict(default_params, world_size=W)
+    P = p3.Engine.make_params(**prm)
+    parts = p3.generate_plummer(W, n, W / 6, seed=11) if plummer else p3.generate_particles(W, n, seed=11)
+    a = p3.Engine(0)
+    a.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_CELLS)
+    a.set_option(_abi.OPT_GRAPH, graph)
+    a.upload(parts, 5)
+    assert np.array_equal(a.slot_of(), np.arange(n))  # identity until the first resident run
+    a.step(P, TS, steps)
+    resident = a.download()
+    slot = a.slot_of()
+    assert not np.array_equal(slot, np.arange(n)) and len(np.unique(slot)) == n and slot.max() < n + 128
+    f_res = a.download_forces()
+    b = p3.Engine(0)
+    b.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_CELLS)
+    cur = parts
+    for _ in range(steps):
+        cur = b.update(P, TS, cur)
+    assert np.array_equal(resident["id"], parts["id"])
+    assert resident.tobytes() == cur.tobytes()
+    # forces of the last step, caller order, through both layouts
+    b.upload(parts, 5)
+    b.step(P, TS, 1)
+    a.upload(parts, 5)
+    a.step(P, TS, 1)
+    assert a.download_forces().tobytes() == b.download_forces().tobytes()
+    assert f_res.shape == (n, 3)
+    # the render buffer and the diagnostics follow the permuted layout too
+    r = a.download_render(W)
+    back = a.download()
+    assert np.array_equal(np.frombuffer(r[16:].tobytes(), dtype=np.float32).reshape(n, 8)[:, 0], back["px"])
+    assert a.diagnostics()["count"] == n
+    a.close()
+    b.close()
+
+
 # ---------------------------------------------------------------- full-size configs against the ORACLE
 def _sample_vs_oracle(prm, parts, out, idx, W, what, tol=1e-5):
     """pos / vel of the sampled particles after one step against the CPU oracle (ideal mode), helpers.py metric."""
