@@ -98,8 +98,10 @@ def test_energy_and_momentum_drift_match_the_oracle(oracle_curves, kernel):
 # reference's sensitivity to nothing but summation order.  The divergence grows like exp(0.084 t) until it
 # saturates near step 300, so K = 8 is a shift of 25 steps along that exponential; the 1e-6 floor covers the first
 # ~60 steps, where the envelope (1e-9) is far below what ANY second f32 implementation can reach (the kernels use
-# rsqrt and a different summation order: 6e-8 measured).  Past saturation only statistics are comparable, so the
-# mean KE of every 100-step window is additionally held to max(K * the oracle's own window deviation, 1e-5).
+# rsqrt and a different summation order: 6e-8 measured).  E(t) saturates (0.24 at step 300, 0.46 at 600: two runs of
+# the ORACLE differ that much), so at t = 300 and 1000 the pointwise bound only says "no blow-up"; what is comparable
+# past the decorrelation time is statistics: the mean KE of every 100-step window is held to
+# max(K * the oracle's own window deviation, 1e-5), and to a factor 2.5 of the oracle's window mean throughout.
 CFG3_N, CFG3_W, CFG3_STEPS, CFG3_K = 262144, 64.0, 1000, 8.0
 CFG3_MARKS = (1, 10, 60, 100, 300, 1000)
 
@@ -150,4 +152,5 @@ def test_config3_1000_step_drift_matches_the_oracle(default_params, kernel):
         dev, bound = abs(m_gpu[k] - m_ref[k]) / m_ref[k], max(CFG3_K * env_w[k], 1e-5)
         report.append(f"window {k*w}-{(k+1)*w}: mean KE dev {dev:.2e} (bound {bound:.2e})")
         assert dev <= bound, f"window {k*w}-{(k+1)*w}: mean KE deviates by {dev:.3e} > {bound:.3e}"
+        assert 0.4 <= m_gpu[k] / m_ref[k] <= 2.5, f"window {k*w}-{(k+1)*w}: mean KE {m_gpu[k]:.4e} vs oracle {m_ref[k]:.4e}"
     print("\n" + "\n".join(report))

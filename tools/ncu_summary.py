@@ -49,12 +49,15 @@ def kernels(path):
 
 
 def main():
-    main_csv = "r01_kernels_n1048576_raw.csv"
+    main_csv = "r02_kernels_n1048576_raw.csv" if os.path.exists(os.path.join(PROF, "r02_kernels_n1048576_raw.csv")) \
+        else "r01_kernels_n1048576_raw.csv"
     top = kernels(os.path.join(PROF, main_csv))[0]
     summary = {"source": f"profiles/{main_csv} (ncu --set full --clock-control none --import-source on, one launch, N=1,048,576)",
                "n_particles": 1048576}
     summary.update(top)
-    for key, name in (("other_kernels_n262144", "r01_kernels_n262144_raw.csv"), ("cell_list_kernels_n1048576", "r01_cells_n1048576_raw.csv"),
+    for key, name in (("other_kernels_n262144", "r01_kernels_n262144_raw.csv"),
+                      ("cell_list_kernels_n1048576", "r02_cells_kernel_n1048576_raw.csv"),
+                      ("cell_list_kernels_n1048576_round1", "r01_cells_n1048576_raw.csv"),
                       ("layout_kernels_n1048576", "r01_layout_n1048576_raw.csv")):
         p = os.path.join(PROF, name)
         if os.path.exists(p):
