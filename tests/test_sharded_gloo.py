@@ -33,7 +33,8 @@ class HostShardEngine:
         ns = self.n_blocks * BLOCK
         self.ids = parts["id"].copy()
         self.pos = [torch.zeros(ns, 4), torch.zeros(ns, 4)]
-        self.vel = np.zeros((ns, 3), np.float32)
+        self.vel_t = torch.zeros(ns, 4)          # like P3D_BUF_VEL: float4 per slot
+        self.vel = self.vel_t.numpy()[:, :3]     # view: the oracle-side code below writes through it
         self.force = torch.zeros(ns, 4)
         self.cur = 0
         self.pos[0][:n, 0] = torch.from_numpy(parts["px"].copy())
@@ -42,7 +43,7 @@ class HostShardEngine:
         self.vel[:n] = np.stack([parts["vx"], parts["vy"], parts["vz"]], 1)
 
     def tensors(self):
-        return {"pos": self.pos[self.cur], "pos_next": self.pos[self.cur ^ 1], "force": self.force}
+        return {"pos": self.pos[self.cur], "pos_next": self.pos[self.cur ^ 1], "force": self.force, "vel": self.vel_t}
 
     def _particles(self):
         a = np.zeros(self.n, O.PARTICLE)
@@ -125,11 +126,12 @@ def test_sharded_stepper_over_gloo(tmp_path, world):
         pos = np.load(tmp_path / f"pos_{r}.npy")
         vel = np.load(tmp_path / f"vel_{r}.npy")
         s0, s1, ncoll = np.load(tmp_path / f"rng_{r}.npy")
-        assert ncoll == 2 * steps  # one all-reduce + one all-gather per step
+        assert ncoll == 3 * steps  # all-reduce(forces) + all-gather(positions) + all-gather(velocities) per step
         # every rank holds every position after the all-gather, bit-identical to the 1-rank oracle run
         assert np.array_equal(pos, refp)
         e = min(s1, n)
-        assert np.array_equal(vel[s0:e], refv[s0:e])  # velocities live on the owning rank
+        # velocities are gathered too: every rank holds the whole state (any rank can serve any part of the array)
+        assert np.array_equal(vel, refv)
         covered[s0:e] = True
     assert covered.all()
     ref2 = p3.generate_particles(12.0, n, seed=4)
