@@ -156,3 +156,88 @@ def test_c_consumer_of_the_multi_device_handle(tmp_path):
         r = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, P3D_DEVICES=devs), timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
         assert "multi_update ok" in r.stdout
+
+
+# ---------------------------------------------------------------- sharded host traffic and shard bookkeeping (one GPU)
+def test_upload_part_commit_and_download_part_on_one_engine(default_params):
+    """p3d_upload_part / p3d_upload_commit / p3d_download_part with world = 1: the parts of the caller's array may
+    arrive in any order and any split; the result equals a plain p3d_upload + p3d_step + p3d_download."""
+    W, n = 25.4, 16384
+    prm = dict(default_params, world_size=W)
+    P = p3.Engine.make_params(**prm)
+    parts = p3.generate_particles(W, n, seed=3)
+    for kernel in (_abi.FORCE_PAIR, _abi.FORCE_CELLS):
+        a = p3.Engine(0)
+        a.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+        a.upload(parts, 5)
+        a.step(P, TS, 2)
+        want = a.download()
+        b = p3.Engine(0)
+        b.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+        for c0, c1 in ((9000, n), (0, 100), (100, 9000)):  # three parts, out of order
+            b.upload_part(parts[c0:c1], c0, n, 5)
+        ptr, cap = b.device_buffer(_abi.BUF_AOS)
+        assert ptr and cap == n
+        b.upload_commit(n)
+        b.step(P, TS, 2)
+        got = np.empty(n, dtype=_abi.PARTICLE)
+        for c0, c1 in ((5000, n), (0, 5000)):
+            b.download_part_into(got[c0:c1], c0)
+        if kernel == _abi.FORCE_CELLS:
+            assert got.tobytes() == want.tobytes()
+        else:  # float atomics: summation order differs run to run
+            dv, dp = parity_errors(got, want, W)
+            assert dv.max() < 1e-4 and dp.max() < 1e-4
+        with pytest.raises(p3.P3DError):
+            b.download_part_into(np.empty(10, dtype=_abi.PARTICLE), n - 5)  # part beyond the resident particles
+        with pytest.raises(p3.P3DError):
+            b.upload_commit(n)  # nothing staged any more
+        with pytest.raises(p3.P3DError):
+            b.upload_part(parts[:10], n - 5, n, 5)  # part beyond n
+        a.close()
+        b.close()
+
+
+def test_set_shard_after_upload_drops_the_layout(default_params):
+    """the slot layout is padded to B * world at upload time; changing `world` afterwards must not leave
+    unequal shards behind - the resident state is dropped and the next step asks for an upload."""
+    prm = dict(default_params)
+    P = p3.Engine.make_params(**prm)
+    parts = p3.generate_particles(10.0, 1000, seed=5)
+    eng = p3.Engine(0)
+    eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_PAIR)
+    eng.upload(parts, 5)
+    eng.set_shard(0, 1)  # same world: the state stays
+    eng.step(P, TS, 1)
+    eng.set_shard(1, 3)  # another world: dropped
+    with pytest.raises(p3.P3DError):
+        eng.shard_force(P)
+    eng.upload(parts, 5)
+    s0, s1 = eng.shard_range()
+    ptr, n_slots = eng.device_buffer(_abi.BUF_POS)
+    assert n_slots % 3 == 0 and (s1 - s0) * 3 == n_slots and s0 == s1 - s0
+    eng.shard_force(P)
+    eng.set_shard(0, 1)
+    eng.upload(np.zeros(0, _abi.PARTICLE), 5)  # empty upload: id_count is still checked by the step
+    with pytest.raises(p3.P3DError):
+        eng.step(p3.Engine.make_params(**dict(prm, id_count=3, attraction_matrix=[0.0] * 9)), TS, 1)
+    eng.step(P, TS, 1)
+    eng.close()
+
+
+def test_slot_of_reports_the_layout(default_params):
+    parts = p3.generate_particles(10.0, 3000, seed=2)
+    eng = p3.Engine(0)
+    eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_CELLS)
+    eng.upload(parts, 5)
+    assert np.array_equal(eng.slot_of(), np.arange(3000))
+    eng.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_PAIR)
+    eng.upload(parts, 5)
+    slot = eng.slot_of()
+    assert len(np.unique(slot)) == 3000
+    order = np.argsort(slot, kind="stable")
+    assert np.all(np.diff(parts["id"][order].astype(np.int64)) >= 0)  # slots are grouped by type ...
+    for t in range(5):
+        idx = np.flatnonzero(parts["id"] == t)
+        assert np.all(np.diff(slot[idx].astype(np.int64)) > 0)       # ... in caller order inside a type
+    eng.close()
