@@ -94,6 +94,7 @@ struct p3d_engine {
     bool typed = false;  // slots are grouped by type (needed by the pair kernel); false: slot = caller index ...
     bool permuted = false;   // ... unless the identity layout was re-slotted into cell order (reslot_by_cell)
     int steps_since_reslot = 0;
+    long long steps_since_upload = 0;  // resident steps taken on the current upload
     std::vector<int> seg_start_h, seg_end_h;
 
     DevBuf<float4> pos[2], vel, frc, spos;
@@ -255,6 +256,7 @@ int build_layout_identity(p3d_engine *e, size_t n, uint32_t T) {
     e->T = T;
     e->typed = false;
     e->permuted = false;
+    e->steps_since_upload = 0;
     e->layout_version++;
     CU(cudaMemsetAsync(e->flags.p, 0, 4 * sizeof(int), e->stream));
     return P3D_OK;
@@ -339,6 +341,7 @@ int layout_finish(p3d_engine *e, size_t n, uint32_t T) {
     // every allocation succeeded: only now does the engine's layout change
     e->typed = true;
     e->permuted = false;
+    e->steps_since_upload = 0;
     e->layout_version++;
     e->B = B;
     e->seg_start_h = seg_start;
@@ -823,7 +826,9 @@ int run_steps(p3d_engine *e, const p3d_params *prm, const DevParams &P, float ts
     e->timed_steps = 0;
     if (e->opt_timing && (rc = ensure_events(e, n_steps))) return rc;
     // device-resident cell-list runs keep their slots in cell order (see reslot_by_cell)
-    const bool reslot = reslot_applies(e) && n_steps >= 2;
+    // (not for the single step of a p3d_update, whose upload is fresh every call; but a caller that keeps the state
+    // resident and steps it one step per call - a render loop - gets it from its third step on)
+    const bool reslot = reslot_applies(e) && (n_steps >= 2 || e->steps_since_upload >= 2);
     auto maybe_reslot = [&]() -> int {
         if (reslot && (!e->permuted || e->steps_since_reslot >= kReslotEvery)) return reslot_by_cell(e, P);
         return P3D_OK;
@@ -854,6 +859,7 @@ int run_steps(p3d_engine *e, const p3d_params *prm, const DevParams &P, float ts
         if ((rc = one_step(e, P, ts, timed, s))) return rc;
         e->steps_since_reslot++;
     }
+    e->steps_since_upload += n_steps;
     return P3D_OK;
 }
 

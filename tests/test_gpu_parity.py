@@ -563,6 +563,29 @@ def test_cell_order_reslot_is_bitwise_transparent(default_params, graph, plummer
     b.close()
 
 
+def test_single_step_calls_on_resident_state_are_reslotted_too(default_params):
+    """A caller that keeps the state resident and steps it one step per call (a render loop) gets the cell-ordered
+    slots from its third step on; a fresh upload per call (p3d_update) never does.  Results are the same bits."""
+    n, W = 50000, 36.8
+    prm = dict(default_params, world_size=W)
+    P = p3.Engine.make_params(**prm)
+    parts = p3.generate_particles(W, n, seed=21)
+    a = p3.Engine(0)
+    a.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_CELLS)
+    a.upload(parts, 5)
+    cur = parts
+    b = p3.Engine(0)
+    b.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_CELLS)
+    for k in range(6):
+        a.step(P, TS, 1)
+        cur = b.update(P, TS, cur)
+        assert np.array_equal(b.slot_of(), np.arange(n))
+        assert (not np.array_equal(a.slot_of(), np.arange(n))) == (k >= 2)
+    assert a.download().tobytes() == cur.tobytes()
+    a.close()
+    b.close()
+
+
 # ---------------------------------------------------------------- full-size configs against the ORACLE
 def _sample_vs_oracle(prm, parts, out, idx, W, what, tol=1e-5):
     """pos / vel of the sampled particles after one step against the CPU oracle (ideal mode), helpers.py metric."""
