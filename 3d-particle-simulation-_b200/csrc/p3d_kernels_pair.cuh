@@ -216,32 +216,89 @@ __device__ __forceinline__ PairConsts make_pair_consts(const DevParams &P) {
 // The i-position enters as a broadcast scalar operand of FADD2 (SASS: `-R.F32`), so it needs no
 // duplication.  Per i-particle: 16 packed FP32 instructions (17 without MPOS) + 2 MUFU.RSQ + 6 FMNMX for
 // four ordered interactions.
+// Source-order knobs of pair_group (tools/pair_search.py explores them on the device: same arithmetic, other
+// operand slots / instruction order in the source, which is all the influence the source has on ptxas' register
+// allocation and operand reuse).  The defaults are the shipped variant.
+#ifndef P3D_PG_FADD_SWAP
+#define P3D_PG_FADD_SWAP 0   // 1: i-position first in the FADD2
+#endif
+#ifndef P3D_PG_D2_ORDER
+#define P3D_PG_D2_ORDER 0    // component order of the d^2 chain: 0 xyz 1 xzy 2 yxz 3 yzx 4 zxy 5 zyx (changes rounding)
+#endif
+#ifndef P3D_PG_LAW_SWAP
+#define P3D_PG_LAW_SWAP 0    // bit 0: constant first in rs, bit 1: constant first in p2
+#endif
+#ifndef P3D_PG_RS_FADD
+#define P3D_PG_RS_FADD 0     // 1: rs = im - inv as FADD2 instead of FFMA2 with -1
+#endif
+#ifndef P3D_PG_ACCI_SWAP
+#define P3D_PG_ACCI_SWAP 0   // 1: relative position first in the i-side accumulations
+#endif
+#ifndef P3D_PG_ACCJ_SWAP
+#define P3D_PG_ACCJ_SWAP 0
+#endif
+#ifndef P3D_PG_ACCI_ORDER
+#define P3D_PG_ACCI_ORDER 0  // component order of the i-side accumulations (as P3D_PG_D2_ORDER; same bits)
+#endif
+#ifndef P3D_PG_ACCJ_ORDER
+#define P3D_PG_ACCJ_ORDER 0
+#endif
+#ifndef P3D_PG_STAGE
+#define P3D_PG_STAGE 0       // 0: all i-side accumulations, then the j-side chains; 1: j-side first; 2: per particle i then j
+#endif
+#ifndef P3D_PG_S_SPLIT
+#define P3D_PG_S_SPLIT 0     // 1: all sij, then all sji
+#endif
+#ifndef P3D_PG_IMM
+#define P3D_PG_IMM 0         // 1: the law's constants as compile-time immediates (default scene: m = 0.3) - probe only
+#endif
+
+template <int K>
+__device__ __forceinline__ void pg_perm(int &a, int &b, int &c) {
+    constexpr int P[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+    a = P[K][0]; b = P[K][1]; c = P[K][2];
+}
+#define P3D_FMA2(SWAP, s, d, acc) ((SWAP) ? __ffma2_rn((d), (s), (acc)) : __ffma2_rn((s), (d), (acc)))
+
 template <int G, bool RCUT, bool MPOS>
 __device__ __forceinline__ void pair_group(const float2 jx, const float2 jy, const float2 jz, const float *nix,
                                            const float *niy, const float *niz, const PairConsts &c,
                                            const float2 aij, const float2 aji, const float r2, float2 *aix,
                                            float2 *aiy, float2 *aiz, float2 &ajx, float2 &ajy, float2 &ajz) {
-    float2 dx[G], dy[G], dz[G], sij[G], sji[G];
+    float2 d[3][G], sij[G], sji[G];
     float2 d2[G], inv[G], rs[G], ti[G];
+#if P3D_PG_IMM
+    const float2 k_im = dup2(1.0f / 0.3f), k_nim = dup2(-1.0f / 0.3f), k_neg1 = dup2(-1.0f), k_tiny = dup2(1.0e-30f);
+#else
+    const float2 k_im = c.im, k_nim = c.nim, k_neg1 = c.neg1, k_tiny = c.tiny;
+#endif
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-        dx[g] = __fadd2_rn(jx, dup2(nix[g]));  // other.position - position (src/lib.rs:211-212, offset 0)
-        dy[g] = __fadd2_rn(jy, dup2(niy[g]));
-        dz[g] = __fadd2_rn(jz, dup2(niz[g]));
+        // other.position - position (src/lib.rs:211-212, offset 0)
+        d[0][g] = P3D_PG_FADD_SWAP ? __fadd2_rn(dup2(nix[g]), jx) : __fadd2_rn(jx, dup2(nix[g]));
+        d[1][g] = P3D_PG_FADD_SWAP ? __fadd2_rn(dup2(niy[g]), jy) : __fadd2_rn(jy, dup2(niy[g]));
+        d[2][g] = P3D_PG_FADD_SWAP ? __fadd2_rn(dup2(niz[g]), jz) : __fadd2_rn(jz, dup2(niz[g]));
     }
+    {
+        int a, b, e;
+        pg_perm<P3D_PG_D2_ORDER>(a, b, e);
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        d2[g] = __ffma2_rn(dx[g], dx[g], c.tiny);
-        d2[g] = __ffma2_rn(dy[g], dy[g], d2[g]);
-        d2[g] = __ffma2_rn(dz[g], dz[g], d2[g]);
+        for (int g = 0; g < G; ++g) {
+            d2[g] = __ffma2_rn(d[a][g], d[a][g], k_tiny);
+            d2[g] = __ffma2_rn(d[b][g], d[b][g], d2[g]);
+            d2[g] = __ffma2_rn(d[e][g], d[e][g], d2[g]);
+        }
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) inv[g] = make_float2(rsqrt_approx(d2[g].x), rsqrt_approx(d2[g].y));
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-        rs[g] = __ffma2_rn(inv[g], c.neg1, c.im);            // u = 1/m - 1/d
+        // u = 1/m - 1/d
+        if (P3D_PG_RS_FADD) rs[g] = __fadd2_rn(k_im, make_float2(-inv[g].x, -inv[g].y));
+        else rs[g] = (P3D_PG_LAW_SWAP & 1) ? __ffma2_rn(k_neg1, inv[g], k_im) : __ffma2_rn(inv[g], k_neg1, k_im);
         if (MPOS) {
-            const float2 p2 = __ffma2_rn(inv[g], c.im, c.nim);   // (1/d - 1) / m
+            // (1/d - 1) / m
+            const float2 p2 = (P3D_PG_LAW_SWAP & 2) ? __ffma2_rn(k_im, inv[g], k_nim) : __ffma2_rn(inv[g], k_im, k_nim);
             ti[g] = make_float2(fmaxf(fminf(rs[g].x, p2.x), 0.0f), fmaxf(fminf(rs[g].y, p2.y), 0.0f));
         } else {
             const float2 p1 = __ffma2_rn(inv[g], c.ncm, c.c2);   // c2 * (1 - m/d)
@@ -254,24 +311,56 @@ __device__ __forceinline__ void pair_group(const float2 jx, const float2 jy, con
             if (!(d2[g].y < r2)) { ti[g].y = 0.0f; rs[g].y = 0.0f; }
         }
     }
+    if (P3D_PG_S_SPLIT) {
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        sij[g] = __ffma2_rn(aij, ti[g], rs[g]);   // f(d; A[i][j]) / d
-        sji[g] = __ffma2_rn(aji, ti[g], rs[g]);   // f(d; A[j][i]) / d
-    }
+        for (int g = 0; g < G; ++g) sij[g] = __ffma2_rn(aij, ti[g], rs[g]);   // f(d; A[i][j]) / d
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        // (scalar pair first: the product commutes, the operand slots ptxas fills do not — 1.6 % on the B200)
-        aix[g] = __ffma2_rn(sij[g], dx[g], aix[g]);   // acc += rel / d * f  (src/lib.rs:231)
-        aiy[g] = __ffma2_rn(sij[g], dy[g], aiy[g]);
-        aiz[g] = __ffma2_rn(sij[g], dz[g], aiz[g]);
-    }
+        for (int g = 0; g < G; ++g) sji[g] = __ffma2_rn(aji, ti[g], rs[g]);   // f(d; A[j][i]) / d
+    } else {
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        ajx = __ffma2_rn(sji[g], dx[g], ajx);         // negated when flushed: rel_ji = -rel_ij
-        ajy = __ffma2_rn(sji[g], dy[g], ajy);
-        ajz = __ffma2_rn(sji[g], dz[g], ajz);
+        for (int g = 0; g < G; ++g) {
+            sij[g] = __ffma2_rn(aij, ti[g], rs[g]);
+            sji[g] = __ffma2_rn(aji, ti[g], rs[g]);
+        }
     }
+    float2 *ai[3] = {aix, aiy, aiz};
+    float2 *aj[3] = {&ajx, &ajy, &ajz};
+    int ia, ib, ic, ja, jb, jc;
+    pg_perm<P3D_PG_ACCI_ORDER>(ia, ib, ic);
+    pg_perm<P3D_PG_ACCJ_ORDER>(ja, jb, jc);
+    // acc += rel / d * f (src/lib.rs:231); the j side is negated when flushed: rel_ji = -rel_ij.
+    // (scalar pair first by default: the product commutes, the operand slots ptxas fills do not — 1.6 % on the B200)
+#define P3D_PG_ISIDE(g)                                                          \
+    do {                                                                         \
+        ai[ia][g] = P3D_FMA2(P3D_PG_ACCI_SWAP, sij[g], d[ia][g], ai[ia][g]);     \
+        ai[ib][g] = P3D_FMA2(P3D_PG_ACCI_SWAP, sij[g], d[ib][g], ai[ib][g]);     \
+        ai[ic][g] = P3D_FMA2(P3D_PG_ACCI_SWAP, sij[g], d[ic][g], ai[ic][g]);     \
+    } while (0)
+#define P3D_PG_JSIDE(g)                                                          \
+    do {                                                                         \
+        *aj[ja] = P3D_FMA2(P3D_PG_ACCJ_SWAP, sji[g], d[ja][g], *aj[ja]);         \
+        *aj[jb] = P3D_FMA2(P3D_PG_ACCJ_SWAP, sji[g], d[jb][g], *aj[jb]);         \
+        *aj[jc] = P3D_FMA2(P3D_PG_ACCJ_SWAP, sji[g], d[jc][g], *aj[jc]);         \
+    } while (0)
+    if (P3D_PG_STAGE == 0) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) P3D_PG_ISIDE(g);
+#pragma unroll
+        for (int g = 0; g < G; ++g) P3D_PG_JSIDE(g);
+    } else if (P3D_PG_STAGE == 1) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) P3D_PG_JSIDE(g);
+#pragma unroll
+        for (int g = 0; g < G; ++g) P3D_PG_ISIDE(g);
+    } else {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            P3D_PG_ISIDE(g);
+            P3D_PG_JSIDE(g);
+        }
+    }
+#undef P3D_PG_ISIDE
+#undef P3D_PG_JSIDE
 }
 
 __device__ __forceinline__ void atomic_add_f3(float4 *dst, float x, float y, float z) {
