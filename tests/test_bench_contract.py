@@ -86,3 +86,23 @@ def test_multi_gpu_roofline_arithmetic():
     assert r["force_pass"]["ms_slowest_rank"] == 41.31 and r["force_pass"]["frac"] > r["frac"]
     # no per-rank diagnostic (--no-fused): the whole-step figures alone
     assert "force_pass" not in bench.multi_gpu_roofline(1048576, 2, 164.3, 148, 1965.0, None)
+
+
+def test_reference_arm_does_not_load_the_product_library_and_configs_match():
+    """the reference arm must build its inputs without libp3d.so (the oracle has its own seeded scenes),
+    and both arms must print the same `config` dict (the driver compares them)."""
+    code = ("import sys, json, io, os; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '3', "
+            "'--particles', '8000']; sys.path.insert(0, %r); import bench; bench.main(); "
+            "maps = open('/proc/self/maps').read(); "
+            "sys.stderr.write('MAPPED:' + ','.join(sorted({l.split('/')[-1] for l in maps.splitlines() if 'libp3d' in l})) + '\\n')") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    mapped = [l for l in r.stderr.splitlines() if l.startswith("MAPPED:")][-1]
+    assert "libp3d_oracle.so" in mapped and "libp3d.so" not in mapped.replace("libp3d_oracle.so", ""), mapped
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][-1])
+    sys.path.insert(0, ROOT)
+    import bench
+
+    W = round(8000.0 ** (1.0 / 3.0), 1)
+    assert d["config"] == bench.config_dict(8000, W, "uniform", False)  # what the engine arm prints for the same args
+    assert d["cpu_cores"] == d["cpu_baseline"]["cores"]
