@@ -158,3 +158,64 @@ def test_sizes_around_block_boundaries(n, default_params):
         e.set_option(_abi.OPT_FORCE_KERNEL, kernel)
         assert_parity(e.update(P, 1 / 60, parts), ideal, W, what=f"n={n} kernel={kernel}")
     e.close()
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_configuration_multi_device(seed):
+    """The same random cases through the multi-device handle (p3d_create_multi): 2, 3 or 4 members (sharing cuda:0 on a
+    one-GPU box, spread over the visible GPUs otherwise), every force kernel, single steps and short resident runs.
+    Covers the split upload + peer all-gather, every kernel's sharding, the fused integrate and the split download
+    on random parameters (walls, gravity, r < 1, m > 1, particles outside the box, T up to 8)."""
+    import torch
+
+    prm, parts, ts = _case(200 + seed)
+    W = prm["world_size"]
+    rng = np.random.default_rng(7000 + seed)
+    members = int(rng.integers(2, 5))
+    ngpu = torch.cuda.device_count()
+    devs = [int(k % ngpu) for k in range(members)]
+    steps = int(rng.choice([1, 1, 3]))
+    ref = parts
+    for _ in range(steps):
+        ref = O.update(prm, ts, ref, mode=O.IDEAL)["out"]
+    e = p3.Engine(devs)
+    P = p3.Engine.make_params(**prm)
+    for kernel in (_abi.FORCE_REFERENCE_ORDER, _abi.FORCE_PAIR, _abi.FORCE_CELLS, _abi.FORCE_AUTO):
+        e.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+        if steps == 1:
+            out = e.update(P, ts, parts)
+        else:
+            e.upload(parts, prm["id_count"])
+            e.step(P, ts, steps)
+            out = e.download()
+        # (errors compound over a resident run: the one-step tolerance per step)
+        assert_parity(out, ref, W, tol=1e-5 * steps, what=f"multi seed {seed} devices {devs} kernel {kernel} steps {steps} {prm}")
+    e.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_resident_cell_runs_with_reslotting(seed):
+    """Random parameters on a resident cell-list run long enough to be re-slotted twice (n >= 32,768, 40 steps):
+    bitwise equal to the same run stepped through fresh uploads."""
+    rng = np.random.default_rng(9000 + seed)
+    prm, _, ts = _case(300 + seed)
+    n = int(rng.choice([32768, 40000, 70001]))
+    W = float(rng.uniform(30.0, 50.0))
+    prm["world_size"] = W
+    prm["particle_effect_radius"] = float(rng.uniform(0.5, 3.0))
+    T = prm["id_count"]
+    parts = p3.generate_plummer(W, n, W / 5, seed=seed, id_count=T) if seed % 2 else p3.generate_particles(W, n, seed=seed, id_count=T)
+    parts["vx"] = rng.normal(0, 1, n).astype(np.float32)
+    P = p3.Engine.make_params(**prm)
+    a = p3.Engine(0)
+    a.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_CELLS)
+    a.upload(parts, T)
+    a.step(P, ts, 40)
+    b = p3.Engine(0)
+    b.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_CELLS)
+    cur = parts
+    for _ in range(40):
+        cur = b.update(P, ts, cur)
+    assert a.download().tobytes() == cur.tobytes(), f"seed {seed} {prm}"
+    a.close()
+    b.close()
