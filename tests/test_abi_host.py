@@ -205,3 +205,18 @@ def test_compiled_consumers_build_and_fail_loudly_without_a_device(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
+
+
+def test_every_kernel_in_the_product_library_is_ours():
+    """No library kernel is left in libp3d.so (round 1 sorted cells with cub::DeviceRadixSort): every device function
+    it carries is one of the hand-written k_* kernels."""
+    import subprocess
+
+    out = subprocess.run(["cuobjdump", "-res-usage", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    names = [l.split("Function ")[1].rstrip(":") for l in out.splitlines() if "Function " in l]
+    assert len(names) >= 35
+    dem = subprocess.run(["c++filt"], input="\n".join(names), capture_output=True, text=True, check=True).stdout.splitlines()
+    for d in dem:
+        base = d.replace("void ", "").split("(")[0].split("<")[0].strip()
+        assert base.startswith("k_"), d
+    assert not any("cub" in d for d in dem)
