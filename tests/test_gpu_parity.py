@@ -462,6 +462,17 @@ def test_cpp_host_mirror_headless_stepper(default_params):
     # n = 0 scales the box to W = 0 < 2r: the mirror must "panic" like assert! at src/lib.rs:132 (exit code 101)
     bad = subprocess.run([os.path.join(pkg, "headless"), "0", "1"], capture_output=True, text=True)
     assert bad.returncode == 101 and "world_size" in bad.stderr
+    # P3D_DEVICES: the same binary over a multi-device handle (p3d_create_multi), and P3D_FAITHFUL: the reference's
+    # bucket double visits reproduced (the faithful oracle's kinetic energy after 100 steps)
+    multi = subprocess.run([os.path.join(pkg, "headless"), "1000", "100", "42", "1"], capture_output=True, text=True,
+                           env=dict(os.environ, P3D_DEVICES="0,0,0"))
+    assert multi.returncode == 0, multi.stderr
+    assert abs(json.loads(multi.stdout)["ke"] - g["ideal_ke"][-1]) / g["ideal_ke"][-1] < 1e-4
+    if "faithful_ke" in g.files:
+        faithful = subprocess.run([os.path.join(pkg, "headless"), "1000", "100", "42", "1"], capture_output=True, text=True,
+                                  env=dict(os.environ, P3D_FAITHFUL="1"))
+        assert faithful.returncode == 0, faithful.stderr
+        assert abs(json.loads(faithful.stdout)["ke"] - g["faithful_ke"][-1]) / g["faithful_ke"][-1] < 1e-4
 
 
 def test_whole_step_calls_refuse_a_sharded_engine(default_params):
