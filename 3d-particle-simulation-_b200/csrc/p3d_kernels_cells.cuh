@@ -252,6 +252,11 @@ __device__ __forceinline__ void cell_pair(const float4 q, float px, float py, fl
     if (RCUT || GENERAL) {  // (in GENERAL mode a candidate may be a far image: the cutoff must be explicit)
         if (!(d2 < r2)) { ti = 0.0f; rs = 0.0f; }
     }
+    if (GENERAL) {
+        // a NaN or infinite coordinate (callers may pass anything) fails `d2 > 0 && d2 < r^2` in the reference
+        // (src/lib.rs:216-220) and contributes nothing: the particle is inert.  0 * NaN would poison the sum.
+        if (!(d2 < r2)) { rx = 0.0f; ry = 0.0f; rz = 0.0f; }
+    }
     const float s = fmaf(arow[f2u(q.w)], ti, rs);
     ax = fmaf(rx, s, ax);
     ay = fmaf(ry, s, ay);

@@ -744,3 +744,37 @@ def test_options_round_trip_and_timing(default_params):
     with pytest.raises(p3.P3DError):  # id_count must match the uploaded layout
         e.step(p3.Engine.make_params(**dict(prm, id_count=4, attraction_matrix=[0.0] * 16)), TS, 1)
     e.close()
+
+
+@pytest.mark.parametrize("n,W", [(3000, 14.4), (40000, 34.2)], ids=["3000", "40000"])
+@pytest.mark.parametrize("kernel", KERNELS + [_abi.FORCE_AUTO], ids=IDS + ["auto"])
+def test_nan_and_infinite_coordinates_are_inert(default_params, kernel, n, W):
+    """Callers may pass anything.  In the reference a particle with a NaN or infinite coordinate fails
+    `d2 > 0 && d2 < r^2` against everybody (src/lib.rs:216-220): it feels and exerts no force, and everybody else
+    evolves as if it were not there.  The engine must not let 0 * NaN leak into its neighbours' sums."""
+    prm = dict(default_params, world_size=W)
+    parts = p3.generate_particles(W, n, seed=8)
+    parts["vx"] = 0.25
+    hostile = np.array([7, 1234, n - 1])
+    parts["px"][7] = np.nan
+    parts["py"][1234] = np.inf
+    parts["pz"][n - 1] = -np.inf
+    ref = O.update(prm, TS, parts, mode=O.IDEAL)["out"]
+    sane = np.ones(n, bool)
+    sane[hostile] = False
+    P = p3.Engine.make_params(**prm)
+    for devices in (0, [0, 0]):  # one device, and the multi-device handle
+        e = p3.Engine(devices)
+        e.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+        out = e.update(P, TS, parts)
+        assert np.isfinite(vel(out)[sane]).all() and np.isfinite(pos(out)[sane]).all()
+        assert_parity(out[sane], ref[sane], W, what=f"kernel {kernel} devices {devices}: the sane particles")
+        for k in ("px", "py", "pz", "vx", "vy", "vz"):  # the hostile ones: same non-finite pattern as the reference
+            assert np.array_equal(np.isnan(out[k][hostile]), np.isnan(ref[k][hostile])), k
+            assert np.array_equal(np.isinf(out[k][hostile]), np.isinf(ref[k][hostile])), k
+        # ... and a resident run keeps going (the out-of-box flag stays set, every later step takes the general path)
+        e.upload(parts, 5)
+        e.step(P, TS, 3)
+        out3 = e.download()
+        assert np.isfinite(vel(out3)[sane]).all()
+        e.close()
