@@ -189,9 +189,12 @@ int canonicalise(const p3d_params *prm, DevParams &P) {
     }
     // The force law is non-zero on (0, 1) — and on (0, m) when m > 1, where the repulsion branch d < m
     // (src/lib.rs:56-58) outlives the attraction branch.  The cutoff d < r (src/lib.rs:216-220) bites when r is smaller.
+    // A negative radius (the fields are public) cuts at |r|: the reference compares d^2 with r*r (src/lib.rs:218-219);
+    // only the kick (src/lib.rs:246) sees its sign.
     const float law_range = std::max(1.0f, m);
-    P.rcut = (P.r < law_range) ? 1 : 0;
-    P.reach = std::min(P.r, law_range);
+    const float r_abs = std::fabs(P.r);
+    P.rcut = (r_abs < law_range) ? 1 : 0;
+    P.reach = std::min(r_abs, law_range);
     return P3D_OK;
 }
 

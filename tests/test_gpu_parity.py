@@ -155,6 +155,12 @@ def test_empty_single_and_coincident(eng, default_params, kernel):
         dict(coefficient=1.0),
         dict(walls=True, acceleration=(0.3, -9.8, 1.0)),
         dict(world_size=4.0),                       # W == 2r: every particle is a boundary particle
+        dict(particle_effect_radius=0.0),           # the UI's lower end (main.rs:308-311): nothing interacts
+        dict(particle_effect_radius=-1.5),          # public field: cuts at |r| (r*r, src/lib.rs:218), kicks with the sign
+        dict(min_pull_ratio=-0.5),                  # no repulsion branch at all
+        dict(min_pull_ratio=2.5, particle_effect_radius=3.0),
+        dict(interaction_force=-3.0, coefficient=-1.0),
+        dict(min_pull_ratio=float("nan")),          # every comparison of src/lib.rs:56-60 fails: no forces
     ],
     ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()),
 )
