@@ -219,3 +219,55 @@ def test_random_resident_cell_runs_with_reslotting(seed):
     assert a.download().tobytes() == cur.tobytes(), f"seed {seed} {prm}"
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_session_multi_device_and_resident_cells(seed):
+    """The device-resident session of test_random_device_resident_session (parameters, box size, walls, kernel and
+    step counts change between p3d_step calls; shrinking the box leaves particles outside) on (a) a multi-device
+    handle and (b) a single engine at a size where the cell list re-slots its state and the all-pairs path hands
+    out-of-box steps to the gated cell pipeline."""
+    import torch
+
+    rng = np.random.default_rng(11000 + seed)
+    prm, _, _ = _case(400 + seed)
+    T = prm["id_count"]
+    ngpu = torch.cuda.device_count()
+    for mode in ("multi", "large"):
+        n = 2500 if mode == "multi" else 36000
+        W = prm["world_size"] = float(rng.uniform(14.0, 30.0)) if mode == "multi" else float(rng.uniform(33.0, 45.0))
+        prm["particle_effect_radius"] = float(min(prm["particle_effect_radius"], W / 2))
+        parts = p3.generate_particles(W, n, seed=seed, id_count=T)
+        parts["vy"] = rng.normal(0, 0.5, n).astype(np.float32)
+        if mode == "large":  # a sparse handful outside the box from the start: the gated out-of-box paths run
+            parts["px"][:: n // 50] += np.float32(W)
+        e = p3.Engine([k % ngpu for k in range(3)]) if mode == "multi" else p3.Engine(0)
+        first = _abi.FORCE_PAIR if (mode == "multi" or seed % 2) else _abi.FORCE_CELLS
+        kernels = ([_abi.FORCE_REFERENCE_ORDER, _abi.FORCE_PAIR, _abi.FORCE_CELLS] if first == _abi.FORCE_PAIR
+                   else [_abi.FORCE_CELLS, _abi.FORCE_CELLS, _abi.FORCE_AUTO])  # identity layout: no pair kernel
+        if mode == "large" and first == _abi.FORCE_PAIR:
+            kernels = [_abi.FORCE_PAIR, _abi.FORCE_CELLS]  # (the exact kernel is O(27 N^2): minutes at this size)
+        e.set_option(_abi.OPT_FORCE_KERNEL, first)
+        e.upload(parts, T)
+        ref = parts
+        ts = float(np.float32(1 / 60))
+        for it in range(5):
+            if rng.integers(0, 2):
+                prm["walls"] = not prm["walls"]
+            if rng.integers(0, 2):
+                # (at 36,000 particles the box only grows: shrinking it with walls on clamps thousands of particles
+                # onto the faces, and the violent pile-up that follows amplifies rounding beyond any per-step bound)
+                lo = 0.8 if mode == "multi" else 1.0
+                prm["world_size"] = float(max(2 * prm["particle_effect_radius"], W * rng.uniform(lo, 1.3)))
+            prm["min_pull_ratio"] = float(rng.uniform(0, 1))
+            prm["attraction_matrix"] = [float(x) for x in rng.uniform(-1, 1, T * T)]
+            e.set_option(_abi.OPT_FORCE_KERNEL, int(rng.choice(kernels)))
+            steps = int(rng.choice([1, 2, 7]))
+            e.step(p3.Engine.make_params(**prm), ts, steps)
+            for _ in range(steps):
+                ref = O.update(prm, ts, ref, mode=O.IDEAL)["out"]
+            out = e.download()
+            assert_parity(out, ref, prm["world_size"], tol=1e-5 * max(1, steps) * 2,
+                          what=f"{mode} session {seed} iteration {it} {prm}")
+            ref = out
+        e.close()
