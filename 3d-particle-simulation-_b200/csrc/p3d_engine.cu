@@ -426,6 +426,7 @@ int build_cells(p3d_engine *e, const DevParams &P, const float4 *pos, int *flag_
         return P3D_OK;
     }
     const size_t ncell = (size_t)(nc * nc * nc);
+    if ((size_t)ns >= (size_t)kCellIndexMask) return fail(P3D_ERR_INVALID, "the cell list handles up to 2^27 slots");
     const int L = (int)ncell + 1;                       // + the ghost bin
     const int tiles = (L + kScanTile - 1) / kScanTile;
     int rc;

@@ -274,16 +274,18 @@ __device__ __forceinline__ void cell_pair(const float4 q, float px, float py, fl
 //      same time) and write the sorted indices of their candidates into a per-thread list in shared memory;
 //   B  one flat loop over the list: one candidate per trip, the next one already in flight; a warp iterates
 //      max-over-lanes(total candidates) times, ~40 at density 1 against a mean of 27, with no control flow inside.
-// Lanes in a y/z face row (their rows wrap, the image differs per row), lanes whose list would overflow (dense
-// regions: long runs amortise the switches anyway) and the GENERAL variant take the direct per-run loop instead.
-// The candidate ORDER is the same in both paths and the same as before (rows z-major, the wrap cell after the row's
-// main run), so the forces do not depend on which path a lane takes.
+// Lanes whose list would overflow (dense regions: long runs amortise the switches anyway) and the GENERAL variant
+// take the direct per-run loop instead.  The candidate ORDER is the same on both paths (the nine rows z-major, then
+// the nine cells behind the x face for edge cells), so the forces do not depend on which path a lane takes.
 constexpr int kCellThreads = 128;
 // 48 entries (24 KB per CTA) with 8 resident CTAs per SM measured best on the B200 at N = 1M, density 1 (candidates per
 // particle ~ Poisson(27)): 0.179 ms per step against 0.184 (64 entries, 6 CTAs) and 0.207 (40 entries, 10 CTAs, spills)
 constexpr int kCellList = 48;                 // list entries per thread
 constexpr int kCellMinBlocks = 8;
-constexpr uint32_t kCellWrapBit = 0x80000000u;  // list entry: candidate seen through the x face
+constexpr uint32_t kCellWrapBit = 0x80000000u;  // list entry: candidate seen through the x face ...
+constexpr int kCellImgY = 29, kCellImgZ = 27;   // ... and 2 bits each for the y / z image (0: none, 1: +W, 2: -W)
+constexpr uint32_t kCellIndexMask = (1u << 27) - 1u;  // sorted index (n_slots < 2^27)
+constexpr int kCellEdgeReserve = 12;            // list entries kept free for an edge cell's nine wrap cells
 
 template <bool RCUT, bool GENERAL>
 __global__ void __launch_bounds__(kCellThreads, kCellMinBlocks) k_force_cells(const float4 *__restrict__ cpos,
@@ -321,51 +323,90 @@ __global__ void __launch_bounds__(kCellThreads, kCellMinBlocks) k_force_cells(co
         const float pxw = (cx == 0) ? sx3[1] : sx3[2];     // ... sees us at x + W resp. x - W
         float ax = 0.f, ay = 0.f, az = 0.f;
 
-        bool direct = GENERAL || cy == 0 || cy == nc - 1 || cz == 0 || cz == nc - 1;
+        bool direct = GENERAL;
         if (!GENERAL) {
-            // ---- phase A: candidate list (interior rows: no y/z wrap, so a row is plain index arithmetic) ----
+            // ---- phase A: candidate list.  All 18 offsets of the 9 rows are loaded BEFORE any of them is used (one
+            // memory latency instead of nine); rows behind a y/z face carry their image in the entry's flag bits. ----
+            uint32_t lo[9], hi[9], img[9];
+            int total = 0;
+#pragma unroll
+            for (int row9 = 0; row9 < 9; ++row9) {
+                const int dz = row9 / 3 - 1, dy = row9 % 3 - 1;
+                int nz = cz + dz, ny = cy + dy;
+                uint32_t im9 = 0u;
+                if (dz < 0 && nz < 0) { nz += nc; im9 |= 1u << kCellImgZ; }
+                if (dz > 0 && nz >= nc) { nz -= nc; im9 |= 2u << kCellImgZ; }
+                if (dy < 0 && ny < 0) { ny += nc; im9 |= 1u << kCellImgY; }
+                if (dy > 0 && ny >= nc) { ny -= nc; im9 |= 2u << kCellImgY; }
+                const uint32_t row = (uint32_t)((nz * nc + ny) * nc);
+                lo[row9] = __ldg(cell_off + row + x0);
+                hi[row9] = __ldg(cell_off + row + x1 + 1);
+                img[row9] = im9;
+            }
+#pragma unroll
+            for (int row9 = 0; row9 < 9; ++row9) {
+                if (!P3D_SLOT_END_OK(hi[row9])) hi[row9] = lo[row9];  // (self-checking build only)
+                total += (int)(hi[row9] - lo[row9]);
+            }
+            direct = total > kCellList - (x_edge ? kCellEdgeReserve : 0);
             int cnt = 0;
             if (!direct) {
-                const uint32_t centre = (uint32_t)((cz * nc + cy) * nc);
 #pragma unroll
-                for (int row9 = 0; row9 < 9; ++row9) {
-                    const int dz = row9 / 3 - 1, dy = row9 % 3 - 1;
-                    const uint32_t row = centre + (uint32_t)((dz * nc + dy) * nc);
-                    uint32_t j = __ldg(cell_off + row + x0);
-                    uint32_t hi = __ldg(cell_off + row + x1 + 1);
-                    if (!P3D_SLOT_END_OK(hi)) hi = j;  // (self-checking build only)
-                    if (cnt + (int)(hi - j) > kCellList) { direct = true; break; }
-                    for (; j < hi; ++j) cand[cnt++][t] = j;
-                    if (x_edge) {
+                for (int row9 = 0; row9 < 9; ++row9)
+                    for (uint32_t j = lo[row9]; j < hi[row9]; ++j) cand[cnt++][t] = j | img[row9];
+                if (x_edge) {  // the cells behind the x face, after the main runs (same order as the direct loop)
+#pragma unroll 1
+                    for (int row9 = 0; row9 < 9 && !direct; ++row9) {
+                        const int dz = row9 / 3 - 1, dy = row9 - (row9 / 3) * 3 - 1;
+                        int nz = cz + dz, ny = cy + dy;
+                        uint32_t flags9 = kCellWrapBit;  // (recomputed: indexing img[] by a loop variable would spill it)
+                        if (nz < 0) { nz += nc; flags9 |= 1u << kCellImgZ; } else if (nz >= nc) { nz -= nc; flags9 |= 2u << kCellImgZ; }
+                        if (ny < 0) { ny += nc; flags9 |= 1u << kCellImgY; } else if (ny >= nc) { ny -= nc; flags9 |= 2u << kCellImgY; }
+                        const uint32_t row = (uint32_t)((nz * nc + ny) * nc);
                         uint32_t jw = __ldg(cell_off + row + xw), hw = __ldg(cell_off + row + xw + 1);
                         if (!P3D_SLOT_END_OK(hw)) hw = jw;
                         if (cnt + (int)(hw - jw) > kCellList) { direct = true; break; }
-                        for (; jw < hw; ++jw) cand[cnt++][t] = jw | kCellWrapBit;
+                        for (; jw < hw; ++jw) cand[cnt++][t] = jw | flags9;
                     }
                 }
             }
-            // ---- phase B: flat loop over the list, the next candidate's load issued before this one is evaluated ----
+            // ---- phase B: flat loop over the list, the next candidate's load issued before this one is evaluated.
+            // Warps without a lane in a y/z face row (nearly all) skip the y/z image decode. ----
+            const bool face = cy == 0 || cy == nc - 1 || cz == 0 || cz == nc - 1;  // (y/z images; the x image is one select)
             if (!direct && cnt > 0) {
                 uint32_t e = cand[0][t];
-                float4 q = __ldg(cpos + (e & ~kCellWrapBit));
-                for (int i = 0; i < cnt; ++i) {
-                    const uint32_t e_next = cand[min(i + 1, cnt - 1)][t];
-                    const float4 q_next = __ldg(cpos + (e_next & ~kCellWrapBit));
-                    const float px = (e & kCellWrapBit) ? pxw : pi.x;
-                    cell_pair<RCUT, false>(q, px, pi.y, pi.z, sx3, sy3, sz3, arow, c2, ncm, nc2, im, r2, ax, ay, az);
-                    e = e_next;
-                    q = q_next;
+                float4 q = __ldg(cpos + (e & kCellIndexMask));
+                if (__any_sync(__activemask(), face)) {
+                    for (int i = 0; i < cnt; ++i) {
+                        const uint32_t e_next = cand[min(i + 1, cnt - 1)][t];
+                        const float4 q_next = __ldg(cpos + (e_next & kCellIndexMask));
+                        const uint32_t iy = (e >> kCellImgY) & 3u, iz = (e >> kCellImgZ) & 3u;
+                        const float px = (e & kCellWrapBit) ? pxw : pi.x;
+                        const float py = iy == 0u ? sy3[0] : (iy == 1u ? sy3[1] : sy3[2]);
+                        const float pz = iz == 0u ? sz3[0] : (iz == 1u ? sz3[1] : sz3[2]);
+                        cell_pair<RCUT, false>(q, px, py, pz, sx3, sy3, sz3, arow, c2, ncm, nc2, im, r2, ax, ay, az);
+                        e = e_next;
+                        q = q_next;
+                    }
+                } else {
+                    for (int i = 0; i < cnt; ++i) {
+                        const uint32_t e_next = cand[min(i + 1, cnt - 1)][t];
+                        const float4 q_next = __ldg(cpos + (e_next & kCellIndexMask));
+                        const float px = (e & kCellWrapBit) ? pxw : pi.x;
+                        cell_pair<RCUT, false>(q, px, pi.y, pi.z, sx3, sy3, sz3, arow, c2, ncm, nc2, im, r2, ax, ay, az);
+                        e = e_next;
+                        q = q_next;
+                    }
                 }
             }
         }
         if (direct) {
-            // ---- direct per-run loop: run 2*row = the non-wrapping cells of row (dy,dz), run 2*row + 1 = the cell
-            //      behind the x face (edge cells only); four candidates per trip while a run lasts ----
+            // ---- direct per-run loop (dense regions, the general variant): runs 0-8 = the non-wrapping cells of row
+            //      (dy,dz), runs 9-17 = the cell behind the x face (edge cells only); four candidates per trip ----
             ax = ay = az = 0.f;
-            for (int run = 0; run < 18; ++run) {
-                const bool wrap = run & 1;
-                if (wrap && !x_edge) continue;
-                const int row9 = run >> 1;
+            for (int run = 0; run < (x_edge ? 18 : 9); ++run) {
+                const bool wrap = run >= 9;
+                const int row9 = wrap ? run - 9 : run;
                 const int dz = row9 / 3 - 1, dy = row9 - (row9 / 3) * 3 - 1;
                 int nz = cz + dz, ny = cy + dy;
                 float pz = sz3[0], py = sy3[0];
