@@ -1082,6 +1082,7 @@ int p3d_upload(p3d_engine *e, const p3d_particle *in, size_t n, uint32_t id_coun
     if ((rc = stage_input(e, in, 0, n, n))) return rc;
     if (e->upload_timed) CU(cudaEventRecord(e->ev_call[1], e->stream));
     e->n_staged = 0;
+    e->T_staged = 0;  // (a plain upload discards whatever p3d_upload_part had staged)
     // `in` may be pageable or reused by the caller: upload_commit returns with the stream idle, i.e. after the copy
     return upload_commit(e, n, id_count, false);
 }
@@ -1093,6 +1094,9 @@ int p3d_upload_part(p3d_engine *e, const p3d_particle *part, size_t i_begin, siz
     if ((rc = upload_args_ok(e, part, i_end > i_begin ? 1 : 0, id_count))) return rc;
     if (!e->members.empty() || e->is_member) return fail(P3D_ERR_INVALID, "p3d_upload_part on a multi-device handle: use p3d_upload");
     if (i_begin > i_end || i_end > n) return fail(P3D_ERR_INVALID, "bad part [%zu, %zu) of %zu", i_begin, i_end, n);
+    if (e->T_staged != 0 && (e->n_staged != n || e->T_staged != id_count))
+        return fail(P3D_ERR_INVALID, "p3d_upload_part: an upload of %zu particles (id_count %u) is being staged; commit it "
+                    "before staging one of %zu (id_count %u)", e->n_staged, e->T_staged, n, id_count);
     CU(cudaSetDevice(e->device));
     e->upload_timed = e->opt_timing != 0;
     if (e->upload_timed) {

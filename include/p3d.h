@@ -172,7 +172,9 @@ int p3d_shard_commit(p3d_engine *eng);
 
 /* Sharded host <-> device traffic for one-process-per-GPU drivers: every rank moves only ITS part of the caller's
  * array over its own PCIe link.
- *   p3d_upload_part   -> callers [i_begin, i_end) of n into the staging array (P3D_BUF_AOS); synchronous
+ *   p3d_upload_part   -> callers [i_begin, i_end) of n into the staging array (P3D_BUF_AOS); synchronous.  All parts
+ *                        of one upload name the same n and id_count; the staging array may move when n grows, so
+ *                        query P3D_BUF_AOS after the call, not before
  *   [driver: all-gather P3D_BUF_AOS across ranks (equal parts of ceil(n / world) particles)]
  *   p3d_upload_commit -> layout + pack from the staging array (what p3d_upload does after its copy)
  *   p3d_download_part -> callers [i_begin, i_end) of the resident state (every rank holds the whole state after a

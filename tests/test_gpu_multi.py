@@ -194,6 +194,12 @@ def test_upload_part_commit_and_download_part_on_one_engine(default_params):
             b.upload_commit(n)  # nothing staged any more
         with pytest.raises(p3.P3DError):
             b.upload_part(parts[:10], n - 5, n, 5)  # part beyond n
+        b.upload_part(parts[:10], 0, n, 5)
+        with pytest.raises(p3.P3DError):
+            b.upload_part(parts[:10], 10, n + 1, 5)  # another n while an upload is being staged
+        b.upload(parts, 5)  # a plain upload discards the staged one ...
+        with pytest.raises(p3.P3DError):
+            b.upload_commit(n)  # ... so there is nothing to commit
         a.close()
         b.close()
 
