@@ -148,3 +148,20 @@ def test_shard_arithmetic():
         assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
         rows = np.concatenate([shard_rows(n_blocks, r, world) for r in range(world)])
         assert sorted(rows) == list(range(n_blocks))
+
+
+def test_part_range_tiles_the_callers_array():
+    """The split of the caller's array over ranks (sharded upload / download, multi-device handle): equal parts of
+    ceil(n / world), the last ones short or empty, together exactly [0, n)."""
+    from particle_3d.sharded import part_range
+
+    for n in (0, 1, 7, 1000, 1048576, 1048577):
+        for world in (1, 2, 3, 8):
+            at = 0
+            per = -(-n // world)
+            for r in range(world):
+                c0, c1 = part_range(n, r, world)
+                assert c0 == at and c0 <= c1 <= n and c1 - c0 <= per
+                assert (c1 - c0 == per) or c1 == n  # only the tail may be short
+                at = c1
+            assert at == n
