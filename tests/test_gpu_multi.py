@@ -247,3 +247,29 @@ def test_slot_of_reports_the_layout(default_params):
         idx = np.flatnonzero(parts["id"] == t)
         assert np.all(np.diff(slot[idx].astype(np.int64)) > 0)       # ... in caller order inside a type
     eng.close()
+
+
+def test_long_resident_cell_run_on_the_handle_is_bitwise_the_single_device_run(default_params):
+    """600 resident cell-list steps: the multi-device handle (three members), a single resident engine (re-slotted 18
+    times) and a single engine fed through p3d_update every step end in the SAME bits.  (Cell-list forces are complete
+    on the member that computes them; the fused kernel only adds the other members' zeros.)"""
+    n, W, steps = 60000, 39.1, 600
+    prm = dict(default_params, world_size=W)
+    P = p3.Engine.make_params(**prm)
+    parts = p3.generate_particles(W, n, seed=5)
+    outs = []
+    for devices in ([0, 0, 0], 0):
+        e = p3.Engine(devices)
+        e.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_CELLS)
+        e.upload(parts, 5)
+        e.step(P, TS, steps)
+        outs.append(e.download())
+        e.close()
+    e = p3.Engine(0)
+    e.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_CELLS)
+    cur = parts
+    for _ in range(steps):
+        cur = e.update(P, TS, cur)
+    e.close()
+    assert outs[0].tobytes() == outs[1].tobytes() == cur.tobytes()
+    assert np.isfinite(outs[0]["vx"]).all()
