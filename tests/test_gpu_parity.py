@@ -784,3 +784,36 @@ def test_nan_and_infinite_coordinates_are_inert(default_params, kernel, n, W):
         out3 = e.download()
         assert np.isfinite(vel(out3)[sane]).all()
         e.close()
+
+
+def test_pageable_and_pinned_caller_memory_give_the_same_bits(default_params):
+    """Large transfers from / to ordinary (pageable) caller memory - a Rust Vec, a numpy array - go through the
+    engine's pinned staging buffers and its host copy threads; pinned caller memory is copied directly.  Same bits,
+    also for sizes that are not a whole number of staging chunks and for the parts of a sharded upload."""
+    import torch
+
+    for n in (18725, 200003, 600000):  # just over the staging threshold, a few chunks, many chunks
+        W = round(float(n) ** (1.0 / 3.0), 1)
+        prm = dict(default_params, world_size=W)
+        P = p3.Engine.make_params(**prm)
+        parts = p3.generate_particles(W, n, seed=n)
+        e = p3.Engine(0)
+        e.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_CELLS)
+        out_pageable = e.update(P, TS, parts)
+        hin = torch.empty(n * 28, dtype=torch.uint8).pin_memory()
+        hout = torch.empty(n * 28, dtype=torch.uint8).pin_memory()
+        a_in, a_out = hin.numpy().view(_abi.PARTICLE), hout.numpy().view(_abi.PARTICLE)
+        a_in[:] = parts
+        e.update_into(P, TS, a_in, a_out)
+        assert out_pageable.tobytes() == a_out.tobytes()
+        # sharded upload from pageable parts, part download into pageable memory
+        cut = n // 3 + 1
+        e.upload_part(parts[cut:], cut, n, 5)
+        e.upload_part(parts[:cut], 0, n, 5)
+        e.upload_commit(n)
+        e.step(P, TS, 1)
+        back = np.empty(n, dtype=_abi.PARTICLE)
+        e.download_part_into(back[:cut], 0)
+        e.download_part_into(back[cut:], cut)
+        assert back.tobytes() == a_out.tobytes()
+        e.close()
