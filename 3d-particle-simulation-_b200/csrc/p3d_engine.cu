@@ -258,6 +258,8 @@ struct p3d_engine {
     std::vector<p3d_engine *> members;
     std::vector<cudaEvent_t> ev_bar;   // one per member: recorded at each cross-device barrier
     bool is_member = false;
+    bool solo = false;                 // handle: the resident upload lives on member 0 alone (see multi_upload)
+    size_t multi_cells_min = 8u << 20; // handle: particle count from which the cell-list / exact kernels are sharded
     // peer memory (CUDA IPC or, inside a multi-device handle, plain peer access):
     // [rank][0]=frc, [1]=pos[0], [2]=pos[1], [3]=vel; own entries are the local pointers
     void *peer_ptr[8][4] = {};
@@ -682,7 +684,7 @@ int reslot_by_cell(p3d_engine *e, const DevParams &P) {
 }
 
 bool reslot_applies(const p3d_engine *e) {
-    return !e->typed && e->world == 1 && !e->is_member && e->n >= (size_t)kReslotMin &&
+    return !e->typed && e->world == 1 && e->n >= (size_t)kReslotMin &&
            resolve_force_kernel(e) == P3D_FORCE_CELLS;
 }
 
@@ -1761,6 +1763,7 @@ int p3d_create_multi(const int *devices, int n_dev, p3d_engine **out) {
         return rc;
     }
     grp->world = n_dev;
+    if (const char *env = std::getenv("P3D_MULTI_CELLS_MIN")) grp->multi_cells_min = (size_t)std::strtoull(env, nullptr, 10);
     *out = grp;
     return P3D_OK;
 }
@@ -1788,6 +1791,27 @@ static int multi_upload(p3d_engine *grp, const p3d_particle *in, size_t n, uint3
     int rc;
     grp->n = 0;
     grp->n_slots = 0;
+    // Only the all-pairs kernel has enough work per step to be worth several devices at ordinary sizes: a cell-list
+    // step at N = 1M is 0.15 ms on one device, less than the host needs to issue the launches and cross-device
+    // barriers of a sharded one (and every device would sort all N cells redundantly).  Below multi_cells_min
+    // particles (8M; P3D_MULTI_CELLS_MIN) such an upload therefore lives on member 0 alone, which then steps it like
+    // a one-device engine (CUDA graphs, cell-ordered slots); from there on the work is sharded like the pair kernel's.
+    p3d_engine *m0 = grp->members[0];
+    for (int g = 0; g < G; ++g) {  // no step of the previous state may still be running
+        CU(cudaSetDevice(grp->members[g]->device));
+        CU(cudaStreamSynchronize(grp->members[g]->stream));
+    }
+    grp->solo = resolve_force_kernel_for(m0, n) != P3D_FORCE_PAIR && n < grp->multi_cells_min;
+    m0->world = grp->solo ? 1 : G;
+    if (grp->solo) {
+        CU(cudaSetDevice(m0->device));
+        if ((rc = stage_input(m0, in, 0, n, n))) return rc;
+        if ((rc = upload_commit(m0, n, id_count, false))) return rc;
+        grp->n = n;
+        grp->n_slots = m0->n_slots;
+        grp->T = id_count;
+        return P3D_OK;
+    }
     const size_t per = staged_part(n, G);
     // every member copies ITS part of the caller's array over its own PCIe link ...
     for (int g = 0; g < G; ++g) {
@@ -1845,6 +1869,7 @@ static int multi_step(p3d_engine *grp, const p3d_params *prm, float ts, int n_st
     int rc;
     if ((rc = canonicalise(prm, P))) return rc;
     if (grp->n_slots == 0) return fail(P3D_ERR_INVALID, "no particles uploaded");
+    if (grp->solo) return p3d_step(grp->members[0], prm, ts, n_steps);
     if (prm->id_count != grp->T)
         return fail(P3D_ERR_INVALID, "id_count %u differs from the uploaded layout (%u): upload again", prm->id_count, grp->T);
     for (int g = 0; g < G; ++g) {
@@ -1880,6 +1905,7 @@ static int multi_download(p3d_engine *grp, p3d_particle *out, size_t n) {
     if (n != grp->n) return fail(P3D_ERR_INVALID, "n=%zu but %zu particles are resident", n, grp->n);
     if (n && !out) return fail(P3D_ERR_INVALID, "out is null");
     int rc;
+    if (grp->solo) return download_range(grp->members[0], out, 0, n, true);
     const size_t per = staged_part(n, G);
     // every device holds the whole state; each serves its part of the caller's array over its own PCIe link
     for (int g = 0; g < G; ++g) {
@@ -1899,6 +1925,7 @@ static int multi_download_forces(p3d_engine *grp, float *out_xyz, size_t n) {
     if (!n) return P3D_OK;
     if (!out_xyz) return fail(P3D_ERR_INVALID, "out is null");
     int rc;
+    if (grp->solo) return p3d_download_forces(grp->members[0], out_xyz, n);
     if ((rc = p3d_sync(grp))) return rc;
     p3d_engine *e = grp->members[0];
     CU(cudaSetDevice(e->device));

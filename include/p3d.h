@@ -69,7 +69,10 @@ int p3d_create(int device, p3d_engine **out);
  * Every whole-state call works on the handle (p3d_update, p3d_upload, p3d_step, p3d_download, p3d_download_forces,
  * p3d_download_render, p3d_diagnostics, p3d_sync, options, counters); the p3d_shard_*, p3d_ipc_*, p3d_set_stream,
  * p3d_device_buffer and per-kernel timing calls return P3D_ERR_INVALID on it.  A device may be listed more than once
- * (the members then share it; exercises the same code on a one-GPU box). */
+ * (the members then share it; exercises the same code on a one-GPU box).
+ * What is sharded: the all-pairs kernel (P3D_FORCE_PAIR) always; the cell-list and exact kernels only from 8M
+ * particles (environment P3D_MULTI_CELLS_MIN), because below that one device steps faster than the host can issue
+ * a sharded step - such an upload lives on the first device alone and behaves exactly like a one-device engine. */
 int p3d_create_multi(const int *devices, int n_dev, p3d_engine **out);
 void p3d_destroy(p3d_engine *eng);
 /* Message for the last non-zero return on this thread. */

@@ -104,7 +104,8 @@ int main(void) {
     CHECK(p3d_diagnostics(eng, d_multi) == P3D_OK && p3d_diagnostics(one, d_one) == P3D_OK);
     CHECK(d_multi[5] == (double)n && fabs(d_multi[0] - d_one[0]) <= 1e-4 * d_one[0]);
     uint64_t cnt[4];
-    CHECK(p3d_get_counters(eng, cnt) == P3D_OK && cnt[1] >= 20u * (uint64_t)n_dev && cnt[2] >= 20u * (uint64_t)n_dev);
+    /* (the cell-list run lives on the first device alone unless P3D_MULTI_CELLS_MIN says otherwise) */
+    CHECK(p3d_get_counters(eng, cnt) == P3D_OK && cnt[1] >= 20u && cnt[2] >= 20u);
     p3d_destroy(one);
     p3d_destroy(eng);
     free(cloud); free(out); free(single); free(ref);

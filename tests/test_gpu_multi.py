@@ -20,6 +20,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TS = float(np.float32(1.0 / 60.0))
 
 
+@pytest.fixture(autouse=True, params=["cells_sharded", "cells_on_one_device"])
+def cell_list_placement(request, monkeypatch):
+    """Below 8M particles a handle keeps a cell-list / exact-kernel upload on its first device alone (sharding such a
+    step costs more host time than the step takes); P3D_MULTI_CELLS_MIN = 0 shards it regardless, which is how the
+    sharded cell-list and exact kernels stay covered here.  The all-pairs kernel is sharded either way."""
+    if request.param == "cells_sharded":
+        monkeypatch.setenv("P3D_MULTI_CELLS_MIN", "0")
+    else:
+        monkeypatch.delenv("P3D_MULTI_CELLS_MIN", raising=False)
+    return request.param
+
+
 def _device_lists():
     import torch
 

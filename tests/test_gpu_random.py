@@ -161,13 +161,15 @@ def test_sizes_around_block_boundaries(n, default_params):
 
 
 @pytest.mark.parametrize("seed", range(24))
-def test_random_configuration_multi_device(seed):
+def test_random_configuration_multi_device(seed, monkeypatch):
     """The same random cases through the multi-device handle (p3d_create_multi): 2, 3 or 4 members (sharing cuda:0 on a
     one-GPU box, spread over the visible GPUs otherwise), every force kernel, single steps and short resident runs.
     Covers the split upload + peer all-gather, every kernel's sharding, the fused integrate and the split download
     on random parameters (walls, gravity, r < 1, m > 1, particles outside the box, T up to 8)."""
     import torch
 
+    if seed % 2:  # shard the cell-list / exact kernels too (by default they stay on one device below 8M particles)
+        monkeypatch.setenv("P3D_MULTI_CELLS_MIN", "0")
     prm, parts, ts = _case(200 + seed)
     W = prm["world_size"]
     rng = np.random.default_rng(7000 + seed)
