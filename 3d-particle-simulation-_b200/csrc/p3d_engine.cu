@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -102,24 +103,31 @@ class HostCopyPool {
             std::memcpy(dst, src, bytes);
             return;
         }
-        std::unique_lock<std::mutex> call_lock(call_mutex_);  // one copy at a time (engines on several threads share the pool)
+        // Every copy is its own Job object: a worker that wakes up late still holds the finished job (whose slices
+        // are exhausted) and can never touch the fields or counters of the next one.
+        auto job = std::make_shared<Job>();
+        job->dst = static_cast<char *>(dst);
+        job->src = static_cast<const char *>(src);
+        job->bytes = bytes;
+        job->n_slices = (bytes + kStageSlice - 1) / kStageSlice;
         {
             std::lock_guard<std::mutex> lk(m_);
-            dst_ = static_cast<char *>(dst);
-            src_ = static_cast<const char *>(src);
-            bytes_ = bytes;
-            n_slices_ = (bytes + kStageSlice - 1) / kStageSlice;
-            next_.store(0);
-            done_.store(0);
+            current_ = job;
             generation_.fetch_add(1, std::memory_order_release);
         }
         cv_work_.notify_all();
-        work();
+        run(*job);
         std::unique_lock<std::mutex> lk(m_);
-        cv_done_.wait(lk, [&] { return done_.load() == n_slices_; });
+        cv_done_.wait(lk, [&] { return job->done.load() == job->n_slices; });
     }
 
    private:
+    struct Job {
+        char *dst = nullptr;
+        const char *src = nullptr;
+        size_t bytes = 0, n_slices = 0;
+        std::atomic<size_t> next{0}, done{0};
+    };
     HostCopyPool() {
         int n = 3;
         if (const char *env = std::getenv("P3D_HOST_THREADS")) n = std::max(0, std::min(15, std::atoi(env) - 1));
@@ -135,13 +143,13 @@ class HostCopyPool {
         cv_work_.notify_all();
         for (auto &t : workers_) t.join();
     }
-    void work() {
+    void run(Job &job) {
         for (;;) {
-            const size_t k = next_.fetch_add(1);
-            if (k >= n_slices_) return;
+            const size_t k = job.next.fetch_add(1);
+            if (k >= job.n_slices) return;
             const size_t off = k * kStageSlice;
-            std::memcpy(dst_ + off, src_ + off, std::min(kStageSlice, bytes_ - off));
-            if (done_.fetch_add(1) + 1 == n_slices_) {
+            std::memcpy(job.dst + off, job.src + off, std::min(kStageSlice, job.bytes - off));
+            if (job.done.fetch_add(1) + 1 == job.n_slices) {
                 std::lock_guard<std::mutex> lk(m_);
                 cv_done_.notify_all();
             }
@@ -151,31 +159,27 @@ class HostCopyPool {
         uint64_t seen = 0;
         for (;;) {
             // The chunks of one transfer arrive ~100 us apart: spin that long for the next one before going to
-            // sleep (a condition-variable wake-up per 4 MiB chunk costs as much as copying it).
+            // sleep (a condition-variable wake-up per chunk costs as much as copying it).
             const auto t0 = std::chrono::steady_clock::now();
             bool got = false;
             while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(300)) {
                 if (generation_.load(std::memory_order_acquire) != seen) { got = true; break; }
             }
-            if (!got) {
-                std::unique_lock<std::mutex> lk(m_);
-                cv_work_.wait(lk, [&] { return stop_ || generation_.load() != seen; });
-                if (stop_) return;
-            }
+            std::shared_ptr<Job> job;
             {
-                std::lock_guard<std::mutex> lk(m_);  // the job's fields were written under this lock
+                std::unique_lock<std::mutex> lk(m_);
+                if (!got) cv_work_.wait(lk, [&] { return stop_ || generation_.load() != seen; });
+                if (stop_) return;
                 seen = generation_.load();
+                job = current_;
             }
-            work();
+            if (job) run(*job);
         }
     }
     std::vector<std::thread> workers_;
-    std::mutex m_, call_mutex_;
+    std::mutex m_;
     std::condition_variable cv_work_, cv_done_;
-    char *dst_ = nullptr;
-    const char *src_ = nullptr;
-    size_t bytes_ = 0, n_slices_ = 0;
-    std::atomic<size_t> next_{0}, done_{0};
+    std::shared_ptr<Job> current_;
     std::atomic<uint64_t> generation_{0};
     bool stop_ = false;
 };
