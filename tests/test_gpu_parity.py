@@ -817,3 +817,32 @@ def test_pageable_and_pinned_caller_memory_give_the_same_bits(default_params):
         e.download_part_into(back[cut:], cut)
         assert back.tobytes() == a_out.tobytes()
         e.close()
+
+
+def test_engines_on_several_threads_share_the_host_copy_pool(default_params):
+    """One engine per thread is the threading contract (`&mut self`, src/lib.rs:130); the pinned-staging copy pool is
+    shared by all engines of the process.  Four engines stepping concurrently from pageable arrays must produce the
+    bits of the same runs done one after the other."""
+    import threading
+
+    def run(seed, out):
+        n, W = 150000, 53.1
+        prm = dict(default_params, world_size=W)
+        P = p3.Engine.make_params(**prm)
+        cur = p3.generate_particles(W, n, seed=seed)
+        e = p3.Engine(0)
+        e.set_option(_abi.OPT_FORCE_KERNEL, _abi.FORCE_CELLS)
+        for _ in range(12):
+            cur = e.update(P, TS, cur)
+        out[seed] = cur
+        e.close()
+
+    seq, par = {}, {}
+    for s in (1, 2, 3, 4):
+        run(s, seq)
+    threads = [threading.Thread(target=run, args=(s, par)) for s in (1, 2, 3, 4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert all(seq[s].tobytes() == par[s].tobytes() for s in (1, 2, 3, 4))
