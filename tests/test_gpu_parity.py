@@ -656,6 +656,22 @@ def test_config3_262k_plummer_one_step_vs_oracle(default_params, kernel):
     _sample_vs_oracle(prm, parts, out, idx, W, f"config 3, kernel {kernel}")
 
 
+@pytest.mark.parametrize("kernel", [_abi.FORCE_CELLS, _abi.FORCE_PAIR], ids=["cells", "pair"])
+def test_config5_4m_one_step_vs_oracle(default_params, kernel):
+    """BASELINE config 5's size on one GPU: N = 4,194,304 (W = 161.3), one p3d_update, 16,384 particles strided over
+    the whole index range against the oracle (the all-pairs step is 5 s of GPU time here; the multi-GPU runs of the
+    same size carry bench.py's parity key)."""
+    n, W = 4194304, 161.3
+    prm = dict(default_params, world_size=W)
+    parts = p3.generate_particles(W, n, seed=42)
+    eng = p3.Engine(0)
+    eng.set_option(_abi.OPT_FORCE_KERNEL, kernel)
+    out = eng.update(p3.Engine.make_params(**prm), TS, parts)
+    eng.close()
+    idx = np.arange(0, n, n // 16384)[:16384]
+    _sample_vs_oracle(prm, parts, out, idx, W, f"config 5 size, kernel {kernel}")
+
+
 # ---------------------------------------------------------------- roofline denominator
 def test_fp32_microbenchmark_confirms_the_roofline_denominator():
     """The FP32 roofline uses 148 SMs x 128 lanes x 2 flop x clock; the packed-FFMA2 microbenchmark must
